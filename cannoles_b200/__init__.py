@@ -9,3 +9,6 @@ fallback: constructing a ``B200Struct`` without the library or without a GPU rai
 """
 from .solver import (CaNNOLeSSolver, ExecutionStats, ParamCaNNOLeS, cannoles, newton_system,  # noqa: F401
                      prepare_newton_system, register_linsolve, solve)
+from .linsolve import B200Error, B200Struct  # noqa: E402,F401
+
+register_linsolve("b200", B200Struct)

@@ -1,0 +1,448 @@
+// engine.cu -- host orchestration of the single-system engine (see engine.h, kernels.cuh).
+#include "engine.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+namespace b2 {
+
+char g_last_error[512] = "";
+
+namespace {
+
+template <typename T>
+int upload(T** dptr, const std::vector<T>& v, double& bytes, size_t min_elems = 1) {
+  size_t n = std::max(v.size(), min_elems);
+  B2_CUDA_OK(cudaMalloc((void**)dptr, n * sizeof(T)));
+  if (!v.empty()) B2_CUDA_OK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  bytes += (double)(n * sizeof(T));
+  return 0;
+}
+
+template <typename T>
+int dalloc(T** dptr, size_t n, double& bytes) {
+  n = std::max<size_t>(n, 1);
+  B2_CUDA_OK(cudaMalloc((void**)dptr, n * sizeof(T)));
+  bytes += (double)(n * sizeof(T));
+  return 0;
+}
+
+int small_class(int m) { return m <= 16 ? 0 : (m <= 40 ? 1 : (m <= 72 ? 2 : 3)); }
+int solve_class(int m) { return m <= 32 ? 0 : (m <= 128 ? 1 : (m <= 512 ? 2 : 3)); }
+
+double wall() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+int Engine::build_plan() {
+  const Symbolic& S = sym;
+  std::vector<int32_t> items;
+  fact_launches.clear(); fwd_launches.clear(); bwd_launches.clear();
+  n_small = n_large = 0;
+  auto front_m = [&](int s) { return (int)(S.rptr[s + 1] - S.rptr[s]); };
+  auto front_w = [&](int s) { return (int)(S.scol[s + 1] - S.scol[s]); };
+  for (int l = 0; l < S.nlevels; l++) {
+    std::vector<int32_t> small[4], large, sol[4];
+    int small_mmax[4] = {0, 0, 0, 0}, sol_mmax[4] = {0, 0, 0, 0};
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; q++) {
+      int s = S.level_sn[q];
+      int m = front_m(s);
+      if (m <= (int)small_max_m) {
+        int c = small_class(m);
+        small[c].push_back(s);
+        small_mmax[c] = std::max(small_mmax[c], m);
+        n_small++;
+      } else {
+        large.push_back(s);
+        n_large++;
+      }
+      int c = solve_class(m);
+      sol[c].push_back(s);
+      sol_mmax[c] = std::max(sol_mmax[c], m);
+    }
+    for (int c = 0; c < 4; c++) {
+      if (!small[c].empty()) {
+        Launch L; L.kind = LK_FRONT_SMALL; L.cls = c; L.off = (int64_t)items.size();
+        L.count = (int)small[c].size();
+        L.smem = (int)(((size_t)small_mmax[c] * small_mmax[c] + 2 * (size_t)small_mmax[c]) * sizeof(double));
+        items.insert(items.end(), small[c].begin(), small[c].end());
+        fact_launches.push_back(L);
+      }
+      if (!sol[c].empty()) {
+        Launch L; L.kind = LK_FWD; L.cls = c; L.off = (int64_t)items.size();
+        L.count = (int)sol[c].size();
+        L.smem = (int)(((size_t)sol_mmax[c] + NB) * sizeof(double));
+        items.insert(items.end(), sol[c].begin(), sol[c].end());
+        fwd_launches.push_back(L);
+        L.kind = LK_BWD;
+        bwd_launches.push_back(L);
+      }
+    }
+    if (large.empty()) continue;
+    {
+      Launch L; L.kind = LK_ASSEMBLE_LARGE; L.off = (int64_t)items.size();
+      for (int s : large) {
+        int nblk = (front_m(s) + ASM_COLS - 1) / ASM_COLS;
+        for (int cb = 0; cb < nblk; cb++) { items.push_back(s); items.push_back(cb); L.count++; }
+      }
+      fact_launches.push_back(L);
+    }
+    {
+      Launch L; L.kind = LK_DIAG_FACTOR; L.off = (int64_t)items.size(); L.jb = 0;
+      for (int s : large) { items.push_back(s); L.count++; }
+      fact_launches.push_back(L);
+    }
+    int wmax = 0;
+    for (int s : large) wmax = std::max(wmax, front_w(s));
+    for (int jb = 0; jb < wmax; jb += NB) {
+      Launch T; T.kind = LK_TRSM; T.off = (int64_t)items.size(); T.jb = jb;
+      for (int s : large) {
+        int w = front_w(s), m = front_m(s);
+        if (w <= jb) continue;
+        int nb = std::min(NB, w - jb);
+        int nrows = m - (jb + nb);
+        for (int ch = 0; ch * TRSM_ROWS < nrows; ch++) { items.push_back(s); items.push_back(ch); T.count++; }
+      }
+      if (T.count) fact_launches.push_back(T);
+      Launch U; U.kind = LK_UPDATE; U.off = (int64_t)items.size(); U.jb = jb; U.mode = 0;
+      for (int s : large) {
+        int w = front_w(s), m = front_m(s);
+        if (w <= jb) continue;
+        int nb = std::min(NB, w - jb);
+        int org = jb + nb;
+        if (org >= w) continue;
+        int ntj = (w - org + TILE - 1) / TILE, nti = (m - org + TILE - 1) / TILE;
+        for (int tj = 0; tj < ntj; tj++)
+          for (int ti = tj; ti < nti; ti++) {
+            items.push_back(s); items.push_back(ti); items.push_back(tj); U.count++;
+          }
+      }
+      if (U.count) fact_launches.push_back(U);
+    }
+    {
+      Launch U; U.kind = LK_UPDATE; U.off = (int64_t)items.size(); U.mode = 1;
+      for (int s : large) {
+        int r = front_m(s) - front_w(s);
+        int nt = (r + TILE - 1) / TILE;
+        for (int tj = 0; tj < nt; tj++)
+          for (int ti = tj; ti < nt; ti++) {
+            items.push_back(s); items.push_back(ti); items.push_back(tj); U.count++;
+          }
+      }
+      if (U.count) fact_launches.push_back(U);
+    }
+  }
+  std::reverse(bwd_launches.begin(), bwd_launches.end());
+  if (upload(&d_items, items, bytes_device)) return -1;
+  return 0;
+}
+
+int Engine::init(int dev) {
+  const double t0 = wall();
+  device = dev;
+  B2_CUDA_OK(cudaSetDevice(dev));
+  B2_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (auto& e : ev) B2_CUDA_OK(cudaEventCreate(&e));
+  const Symbolic& S = sym;
+  if ((size_t)(S.max_front + NB) * sizeof(double) > 200 * 1024) {
+    snprintf(g_last_error, sizeof(g_last_error), "front of order %d exceeds the solve kernels' shared memory", S.max_front);
+    return -1;
+  }
+  std::vector<int32_t> slot_ptr32(S.slot_ptr.begin(), S.slot_ptr.end());
+  if (upload(&d_slot_ptr, slot_ptr32, bytes_device)) return -1;
+  if (upload(&d_coo_sorted, S.coo_sorted, bytes_device)) return -1;
+  if (dalloc(&d_vals, (size_t)S.nnz, bytes_device)) return -1;
+  if (dalloc(&d_nzval, (size_t)S.nnzA, bytes_device)) return -1;
+  if (upload(&d_rho_slot, S.rho_slot, bytes_device)) return -1;
+  if (upload(&d_delta_slot, S.delta_slot, bytes_device)) return -1;
+  if (dalloc(&d_rho_base, (size_t)S.nvar, bytes_device)) return -1;
+  if (dalloc(&d_delta_base, (size_t)S.ncon, bytes_device)) return -1;
+  if (upload(&d_scol, S.scol, bytes_device)) return -1;
+  if (upload(&d_rptr, S.rptr, bytes_device)) return -1;
+  if (upload(&d_lptr, S.lptr, bytes_device)) return -1;
+  if (upload(&d_cbptr, S.cbptr, bytes_device)) return -1;
+  if (upload(&d_uptr, S.uptr, bytes_device)) return -1;
+  if (upload(&d_rowidx, S.rowidx, bytes_device)) return -1;
+  if (upload(&d_rel, S.rel, bytes_device)) return -1;
+  if (upload(&d_child_ptr, S.child_ptr, bytes_device)) return -1;
+  if (upload(&d_child_idx, S.child_idx, bytes_device)) return -1;
+  if (upload(&d_amap_ptr, S.amap_ptr, bytes_device)) return -1;
+  if (upload(&d_amap_slot, S.amap_slot, bytes_device)) return -1;
+  if (upload(&d_amap_pos, S.amap_pos, bytes_device)) return -1;
+  if (upload(&d_perm, S.perm, bytes_device)) return -1;
+  if (upload(&d_Sp, S.Sp, bytes_device)) return -1;
+  if (upload(&d_Sj, S.Sj, bytes_device)) return -1;
+  if (upload(&d_Sslot, S.Sslot, bytes_device)) return -1;
+  if (dalloc(&d_Lx, (size_t)S.nnzL_store, bytes_device)) return -1;
+  if (dalloc(&d_CB, (size_t)S.cb_store, bytes_device)) return -1;
+  if (dalloc(&d_dvec, (size_t)S.N, bytes_device)) return -1;
+  if (dalloc(&d_counts, 8, bytes_device)) return -1;
+  d_flags = reinterpret_cast<int*>(d_counts + 4);
+  if (dalloc(&d_x, (size_t)S.N, bytes_device)) return -1;
+  if (dalloc(&d_upd, (size_t)S.uptr[S.nsuper], bytes_device)) return -1;
+  if (dalloc(&d_rhs, (size_t)S.N, bytes_device)) return -1;
+  if (dalloc(&d_sol, (size_t)S.N, bytes_device)) return -1;
+  if (dalloc(&d_res, (size_t)S.N, bytes_device)) return -1;
+  if (dalloc(&d_out, (size_t)S.N, bytes_device)) return -1;
+  if (dalloc(&d_part, 1024 + 8, bytes_device)) return -1;
+  B2_CUDA_OK(cudaMallocHost((void**)&h_counts, 8 * sizeof(unsigned long long)));
+  B2_CUDA_OK(cudaMallocHost((void**)&h_scalars, 8 * sizeof(double)));
+  plan.scol = d_scol; plan.rptr = d_rptr; plan.lptr = d_lptr; plan.cbptr = d_cbptr; plan.uptr = d_uptr;
+  plan.rowidx = d_rowidx; plan.rel = d_rel; plan.child_ptr = d_child_ptr; plan.child_idx = d_child_idx;
+  plan.amap_ptr = d_amap_ptr; plan.amap_slot = d_amap_slot; plan.amap_pos = d_amap_pos;
+  plan.nzval = d_nzval; plan.Lx = d_Lx; plan.CB = d_CB; plan.dvec = d_dvec; plan.flags = d_flags;
+  if (build_plan()) return -1;
+  const int big = 200 * 1024;
+  B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_bwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaDeviceSynchronize());
+  t_plan = wall() - t0;
+  return 0;
+}
+
+void Engine::destroy() {
+#ifndef B2_EMULATE
+  if (g_fact) cudaGraphExecDestroy(g_fact);
+  if (g_fwdbwd) cudaGraphExecDestroy(g_fwdbwd);
+#endif
+  for (void* p : registered) cudaHostUnregister(p);
+  void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
+                  d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
+                  d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
+                  d_counts, d_items, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h_counts) cudaFreeHost(h_counts);
+  if (h_scalars) cudaFreeHost(h_scalars);
+  for (auto& e : ev) if (e) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int Engine::run_factor_launches() {
+  for (const Launch& L : fact_launches) {
+    const int32_t* it = d_items + L.off;
+    switch (L.kind) {
+      case LK_FRONT_SMALL:
+        if (L.cls == 0) B2_LAUNCH(k_front_small<32>, L.count, 32, L.smem, stream, plan, it, L.count);
+        else if (L.cls == 1) B2_LAUNCH(k_front_small<64>, L.count, 64, L.smem, stream, plan, it, L.count);
+        else if (L.cls == 2) B2_LAUNCH(k_front_small<128>, L.count, 128, L.smem, stream, plan, it, L.count);
+        else B2_LAUNCH(k_front_small<256>, L.count, 256, L.smem, stream, plan, it, L.count);
+        break;
+      case LK_ASSEMBLE_LARGE:
+        B2_LAUNCH(k_assemble_large, L.count, 256, 0, stream, plan, it, L.count);
+        break;
+      case LK_DIAG_FACTOR:
+        B2_LAUNCH(k_diag_factor, L.count, 32, 0, stream, plan, it, L.count, L.jb);
+        break;
+      case LK_TRSM:
+        B2_LAUNCH(k_trsm, L.count, TRSM_ROWS, 0, stream, plan, it, L.count, L.jb);
+        break;
+      case LK_UPDATE:
+        B2_LAUNCH(k_update, L.count, 256, 0, stream, plan, it, L.count, L.jb, NB, L.mode);
+        break;
+      default: break;
+    }
+  }
+  B2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int Engine::run_solve_launches() {
+  for (int pass = 0; pass < 2; pass++) {
+    const std::vector<Launch>& LL = pass == 0 ? fwd_launches : bwd_launches;
+    for (const Launch& L : LL) {
+      const int32_t* it = d_items + L.off;
+      if (pass == 0) {
+        if (L.cls == 0) B2_LAUNCH(k_fwd<32>, L.count, 32, L.smem, stream, plan, it, L.count, d_x, d_upd);
+        else if (L.cls == 1) B2_LAUNCH(k_fwd<64>, L.count, 64, L.smem, stream, plan, it, L.count, d_x, d_upd);
+        else if (L.cls == 2) B2_LAUNCH(k_fwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x, d_upd);
+        else B2_LAUNCH(k_fwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x, d_upd);
+      } else {
+        if (L.cls == 0) B2_LAUNCH(k_bwd<32>, L.count, 32, L.smem, stream, plan, it, L.count, d_x);
+        else if (L.cls == 1) B2_LAUNCH(k_bwd<64>, L.count, 64, L.smem, stream, plan, it, L.count, d_x);
+        else if (L.cls == 2) B2_LAUNCH(k_bwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x);
+        else B2_LAUNCH(k_bwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x);
+      }
+    }
+  }
+  B2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int Engine::assemble_and_factor(double eig_tol, int64_t* npos, int64_t* nzero, int64_t* nneg,
+                                int* breakdown, bool do_assemble) {
+  const Symbolic& S = sym;
+  B2_CUDA_OK(cudaEventRecord(ev[1], stream));
+  if (do_assemble) {
+    const int nb = (int)((S.nnzA + 255) / 256);
+    B2_LAUNCH(k_assemble_csc, nb, 256, 0, stream, S.nnzA, d_slot_ptr, d_coo_sorted, d_vals, d_nzval);
+    if (S.shift_ok) {
+      if (S.nvar > 0)
+        B2_LAUNCH(k_diag_base, (int)((S.nvar + 255) / 256), 256, 0, stream, (int)S.nvar, d_rho_slot,
+                  d_slot_ptr, d_coo_sorted, d_vals, d_rho_base);
+      if (S.ncon > 0)
+        B2_LAUNCH(k_diag_base, (int)((S.ncon + 255) / 256), 256, 0, stream, (int)S.ncon, d_delta_slot,
+                  d_slot_ptr, d_coo_sorted, d_vals, d_delta_base);
+    }
+  }
+  B2_CUDA_OK(cudaEventRecord(ev[2], stream));
+  B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
+#ifndef B2_EMULATE
+  if (use_graph) {
+    if (!g_fact) {
+      cudaGraph_t g;
+      B2_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      int rc = run_factor_launches();
+      cudaError_t ce = cudaStreamEndCapture(stream, &g);
+      if (rc || ce != cudaSuccess) {
+        snprintf(g_last_error, sizeof(g_last_error), "graph capture of the factorization failed: %s",
+                 cudaGetErrorString(ce));
+        return -1;
+      }
+      B2_CUDA_OK(cudaGraphInstantiate(&g_fact, g, 0));
+      cudaGraphDestroy(g);
+    }
+    B2_CUDA_OK(cudaGraphLaunch(g_fact, stream));
+  } else
+#endif
+  {
+    if (run_factor_launches()) return -1;
+  }
+  {
+    int nb = (int)std::min<int64_t>((S.N + 255) / 256, 1184);
+    B2_LAUNCH(k_inertia, nb, 256, 0, stream, d_dvec, S.N, eig_tol, d_counts);
+  }
+  B2_CUDA_OK(cudaEventRecord(ev[3], stream));
+  B2_CUDA_OK(cudaMemcpyAsync(h_counts, d_counts, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_OK(cudaStreamSynchronize(stream));
+  B2_CUDA_OK(cudaGetLastError());
+  if (npos) *npos = (int64_t)h_counts[0];
+  if (nzero) *nzero = (int64_t)h_counts[1];
+  if (nneg) *nneg = (int64_t)h_counts[2];
+  if (breakdown) *breakdown = (int)(h_counts[4] & 0xffffffffull) != 0;
+  factored = true;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]); last_ms[0] = ms;
+  cudaEventElapsedTime(&ms, ev[1], ev[2]); last_ms[1] = ms;
+  cudaEventElapsedTime(&ms, ev[2], ev[3]); last_ms[2] = ms;
+  return 0;
+}
+
+int Engine::factorize_host(const double* vals, double eig_tol, int64_t* npos, int64_t* nzero,
+                           int64_t* nneg, int* breakdown) {
+  B2_CUDA_OK(cudaSetDevice(device));
+  B2_CUDA_OK(cudaEventRecord(ev[0], stream));
+  B2_CUDA_OK(cudaMemcpyAsync(d_vals, vals, (size_t)sym.nnz * sizeof(double), cudaMemcpyHostToDevice, stream));
+  have_vals = true;
+  return assemble_and_factor(eig_tol, npos, nzero, nneg, breakdown, true);
+}
+
+int Engine::factorize_dev(const double* d_vals_in, double eig_tol, int64_t* npos, int64_t* nzero,
+                          int64_t* nneg, int* breakdown) {
+  B2_CUDA_OK(cudaSetDevice(device));
+  B2_CUDA_OK(cudaEventRecord(ev[0], stream));
+  if (d_vals_in != d_vals)
+    B2_CUDA_OK(cudaMemcpyAsync(d_vals, d_vals_in, (size_t)sym.nnz * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  have_vals = true;
+  return assemble_and_factor(eig_tol, npos, nzero, nneg, breakdown, true);
+}
+
+int Engine::refactorize_shift(double rho, double delta, double eig_tol, int64_t* npos, int64_t* nzero,
+                              int64_t* nneg, int* breakdown) {
+  const Symbolic& S = sym;
+  if (!S.shift_ok) {
+    snprintf(g_last_error, sizeof(g_last_error), "COO layout has no canonical rho/delta segments; re-upload with b2_factorize");
+    return -2;
+  }
+  if (!have_vals) {
+    snprintf(g_last_error, sizeof(g_last_error), "b2_refactorize_shift before any b2_factorize");
+    return -2;
+  }
+  B2_CUDA_OK(cudaSetDevice(device));
+  B2_CUDA_OK(cudaEventRecord(ev[0], stream));
+  if (S.nvar > 0)
+    B2_LAUNCH(k_diag_shift, (int)((S.nvar + 255) / 256), 256, 0, stream, (int)S.nvar, d_rho_slot, d_rho_base, rho, d_nzval);
+  if (S.ncon > 0 && delta == delta)
+    B2_LAUNCH(k_diag_shift, (int)((S.ncon + 255) / 256), 256, 0, stream, (int)S.ncon, d_delta_slot, d_delta_base, -delta, d_nzval);
+  return assemble_and_factor(eig_tol, npos, nzero, nneg, breakdown, false);
+}
+
+int Engine::solve_core(const double* d_b, double* d_o, int negate, int refine_steps, double* relres) {
+  const Symbolic& S = sym;
+  const int64_t N = S.N;
+  const int nb = (int)((N + 255) / 256);
+  if (!factored) {
+    snprintf(g_last_error, sizeof(g_last_error), "b2_solve before a factorization");
+    return -2;
+  }
+  auto one_solve = [&](const double* b, int accumulate) -> int {
+    B2_LAUNCH(k_perm_in, nb, 256, 0, stream, N, d_perm, b, d_x);
+#ifndef B2_EMULATE
+    if (use_graph) {
+      if (!g_fwdbwd) {
+        cudaGraph_t g;
+        B2_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_solve_launches();
+        cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        if (rc || ce != cudaSuccess) {
+          snprintf(g_last_error, sizeof(g_last_error), "graph capture of the solve failed: %s", cudaGetErrorString(ce));
+          return -1;
+        }
+        B2_CUDA_OK(cudaGraphInstantiate(&g_fwdbwd, g, 0));
+        cudaGraphDestroy(g);
+      }
+      B2_CUDA_OK(cudaGraphLaunch(g_fwdbwd, stream));
+    } else
+#endif
+    {
+      if (run_solve_launches()) return -1;
+    }
+    B2_LAUNCH(k_perm_out, nb, 256, 0, stream, N, d_perm, d_x, d_sol, accumulate);
+    return 0;
+  };
+  if (one_solve(d_b, 0)) return -1;
+  const bool need_res = refine_steps > 0 || relres != nullptr;
+  for (int it = 0; it <= refine_steps && need_res; it++) {
+    B2_LAUNCH(k_residual, nb, 256, 0, stream, N, d_Sp, d_Sj, d_Sslot, d_nzval, d_sol, d_b, d_res);
+    if (it == refine_steps) break;
+    if (one_solve(d_res, 1)) return -1;
+  }
+  if (relres) {
+    int pb = (int)std::min<int64_t>(nb, 512);
+    B2_LAUNCH(k_sumsq, pb, 256, 0, stream, N, d_res, d_part);
+    B2_LAUNCH(k_fold, 1, 256, 0, stream, pb, d_part, d_part + 1024);
+    B2_LAUNCH(k_sumsq, pb, 256, 0, stream, N, d_b, d_part);
+    B2_LAUNCH(k_fold, 1, 256, 0, stream, pb, d_part, d_part + 1025);
+    B2_CUDA_OK(cudaMemcpyAsync(h_scalars, d_part + 1024, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  }
+  B2_LAUNCH(k_scale_copy, nb, 256, 0, stream, N, d_sol, d_o, negate ? -1.0 : 1.0);
+  B2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int Engine::solve_host(const double* rhs, double* out, int negate, int refine_steps, double* relres) {
+  B2_CUDA_OK(cudaSetDevice(device));
+  const size_t nbytes = (size_t)sym.N * sizeof(double);
+  B2_CUDA_OK(cudaEventRecord(ev[0], stream));
+  B2_CUDA_OK(cudaMemcpyAsync(d_rhs, rhs, nbytes, cudaMemcpyHostToDevice, stream));
+  B2_CUDA_OK(cudaEventRecord(ev[1], stream));
+  if (solve_core(d_rhs, d_out, negate, refine_steps, relres)) return -1;
+  B2_CUDA_OK(cudaEventRecord(ev[4], stream));
+  B2_CUDA_OK(cudaMemcpyAsync(out, d_out, nbytes, cudaMemcpyDeviceToHost, stream));
+  B2_CUDA_OK(cudaEventRecord(ev[5], stream));
+  B2_CUDA_OK(cudaStreamSynchronize(stream));
+  if (relres) *relres = h_scalars[1] > 0 ? std::sqrt(h_scalars[0] / h_scalars[1]) : std::sqrt(h_scalars[0]);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]); last_ms[0] = ms;
+  cudaEventElapsedTime(&ms, ev[1], ev[4]); last_ms[3] = ms;
+  cudaEventElapsedTime(&ms, ev[4], ev[5]); last_ms[4] = ms;
+  return 0;
+}
+
+}  // namespace b2

@@ -1,0 +1,90 @@
+// engine.h -- host side of the single-system engine: owns the symbolic plan, the device
+// buffers, the per-level launch lists and (on a GPU) the CUDA graphs that replay them.
+#pragma once
+#include <vector>
+
+#include "b2_cuda.h"
+#include "plan.h"
+#include "symbolic.h"
+
+namespace b2 {
+
+enum LaunchKind : int {
+  LK_FRONT_SMALL = 0,
+  LK_ASSEMBLE_LARGE,
+  LK_DIAG_FACTOR,
+  LK_TRSM,
+  LK_UPDATE,
+  LK_FWD,
+  LK_BWD,
+};
+
+struct Launch {
+  int kind = 0;
+  int cls = 0;        // thread-count class for per-front kernels (0:32 1:64 2:128 3:256)
+  int64_t off = 0;    // offset into the device item buffer (in int32 units)
+  int count = 0;      // items == CTAs
+  int jb = 0;         // pivot block origin (tiled path)
+  int mode = 0;       // k_update mode
+  int smem = 0;       // dynamic shared memory (bytes)
+};
+
+struct Engine {
+  Symbolic sym;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double small_max_m = 128;  // fronts up to this order take the shared-memory path
+
+  // device buffers
+  int32_t *d_slot_ptr = nullptr, *d_coo_sorted = nullptr;
+  double *d_vals = nullptr, *d_nzval = nullptr;
+  int32_t *d_rho_slot = nullptr, *d_delta_slot = nullptr;
+  double *d_rho_base = nullptr, *d_delta_base = nullptr;
+  int32_t *d_scol = nullptr, *d_rowidx = nullptr, *d_rel = nullptr, *d_child_ptr = nullptr,
+          *d_child_idx = nullptr, *d_amap_slot = nullptr, *d_amap_pos = nullptr, *d_perm = nullptr;
+  int64_t *d_rptr = nullptr, *d_lptr = nullptr, *d_cbptr = nullptr, *d_uptr = nullptr,
+          *d_amap_ptr = nullptr;
+  double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr;
+  int* d_flags = nullptr;
+  unsigned long long* d_counts = nullptr;
+  int32_t* d_items = nullptr;
+  // solve
+  double *d_x = nullptr, *d_upd = nullptr, *d_rhs = nullptr, *d_sol = nullptr, *d_res = nullptr,
+         *d_out = nullptr, *d_part = nullptr;
+  int64_t* d_Sp = nullptr;
+  int32_t *d_Sj = nullptr, *d_Sslot = nullptr;
+  // pinned host mirrors
+  unsigned long long* h_counts = nullptr;  // [0..3] counts, [4] breakdown flag
+  double* h_scalars = nullptr;
+
+  PlanDev plan{};
+  std::vector<Launch> fact_launches, fwd_launches, bwd_launches;
+  int64_t n_small = 0, n_large = 0;
+  double bytes_device = 0, t_plan = 0;
+  bool have_vals = false, factored = false;
+  double last_ms[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+#ifndef B2_EMULATE
+  cudaGraphExec_t g_fact = nullptr, g_fwdbwd = nullptr;
+#endif
+  bool use_graph = true;
+  std::vector<void*> registered;
+
+  int init(int dev);
+  void destroy();
+  int build_plan();
+  int run_factor_launches();
+  int run_solve_launches();
+  int assemble_and_factor(double eig_tol, int64_t* npos, int64_t* nzero, int64_t* nneg, int* breakdown,
+                          bool do_assemble);
+  int factorize_host(const double* vals, double eig_tol, int64_t* npos, int64_t* nzero, int64_t* nneg,
+                     int* breakdown);
+  int factorize_dev(const double* d_vals_in, double eig_tol, int64_t* npos, int64_t* nzero,
+                    int64_t* nneg, int* breakdown);
+  int refactorize_shift(double rho, double delta, double eig_tol, int64_t* npos, int64_t* nzero,
+                        int64_t* nneg, int* breakdown);
+  int solve_core(const double* d_b, double* d_o, int negate, int refine_steps, double* relres);
+  int solve_host(const double* rhs, double* out, int negate, int refine_steps, double* relres);
+};
+
+}  // namespace b2

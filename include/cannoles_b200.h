@@ -1,0 +1,154 @@
+/*
+ * cannoles_b200.h -- C ABI of libcannoles_b200.so, the B200 (sm_100a) `linsolve` backend for the
+ * KKT factor/solve path of CaNNOLeS.jl.
+ *
+ * Each entry point replaces one step of the reference's linear-solver struct interface
+ * (reference/src/solver_types.jl); INTEGRATION.md shows the Julia `ccall` glue.
+ *
+ *   b2_analyze            <-  LDLFactStruct(N, rows, cols, vals) ctor: `sparse`+`triu`+`ldl_analyze`
+ *                             (src/solver_types.jl:61-65, called at src/CaNNOLeS.jl:327)
+ *   b2_factorize          <-  try_to_factorize: set_vals! + ldl_factorize! + inertia loop
+ *                             (src/solver_types.jl:79-98; set_vals! :53-59)
+ *   b2_refactorize_shift  <-  the rho / delta retry of newton_system! (src/CaNNOLeS.jl:1029-1043),
+ *                             which in the reference is a full try_to_factorize again
+ *   b2_solve              <-  solve_ldl!: ldiv! then negate (src/solver_types.jl:69-77)
+ *   b2_free               <-  Julia finalizer of the struct
+ *   b2b_*                 <-  the same verbs for a batch of independent KKT systems sharing one
+ *                             sparsity pattern (no counterpart in the reference: multi-start /
+ *                             per-sample estimation, BASELINE.json config 5)
+ *
+ * Conventions: every function returns 0 on success and a negative value on a runtime error
+ * (CUDA failure, malformed input); `b2_last_error()` describes it.  NUMERICAL failure (wrong
+ * inertia, zero pivot) is NOT an error: it is reported through the out-parameters, as the
+ * reference reports it through the Bool of try_to_factorize (src/solver_types.jl:96-97).
+ * All host pointers are plain C arrays owned by the caller; indices are 1-based Int64 exactly as
+ * CaNNOLeS builds them (src/CaNNOLeS.jl:276-315); values are Float64.  The library is not
+ * re-entrant per handle (the reference drives it from one thread).  There is no CPU fallback:
+ * without a CUDA device every call fails.
+ */
+#ifndef CANNOLES_B200_H
+#define CANNOLES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_handle b2_handle;   /* one KKT system: symbolic plan + device factor */
+typedef struct b2b_handle b2b_handle; /* a batch of systems with one shared pattern      */
+
+/* orderings for b2_analyze / b2b_analyze */
+#define B2_ORDER_ND 0      /* nested dissection (default)                       */
+#define B2_ORDER_NATURAL 1 /* identity                                          */
+#define B2_ORDER_USER 2    /* user_perm[k] = 0-based original index of pivot k  */
+#define B2_ORDER_AMD 3     /* approximate minimum degree                        */
+
+typedef struct {
+  int64_t N, nnz, nnzA;           /* order, COO entries, distinct upper-triangular positions   */
+  int64_t nnzL;                   /* exact off-diagonal nonzeros of L (no padding)             */
+  int64_t nnzL_store, cb_store;   /* doubles held by the factor panels / contribution blocks   */
+  int64_t nsuper, nlevels;        /* fronts (supernodes) and assembly-tree levels              */
+  int64_t max_front, max_width;   /* largest front order and pivot-block width                 */
+  int64_t n_small, n_large;       /* fronts on the shared-memory path / the tiled path         */
+  int64_t launches_factor, launches_solve; /* kernel launches per factorize / per solve        */
+  double flops;                   /* sum_j (c_j^2 + 3 c_j), exact symbolic       */
+  double flops_store;             /* flops executed on the dense fronts (with padding)         */
+  double t_order, t_symbolic, t_plan; /* seconds spent in ordering / symbolic / device set-up  */
+  double bytes_device;            /* device memory held by the handle                          */
+} b2_stats_t;
+
+const char* b2_last_error(void);
+int b2_version(void);
+int b2_device_count(void);
+
+/* Symbolic analysis, once per solver.  rows1/cols1: COO lower triangle (rows1[t] >= cols1[t]),
+ * 1-based, duplicates allowed; a strictly-upper entry is rejected (the reference's `triu`
+ * would silently drop it).  nvar/nequ/ncon give the block sizes (N = nvar+nequ+ncon) so that the
+ * trailing -delta / rho diagonal segments of the COO layout can be shifted on the device. */
+int b2_analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* cols1, int64_t nvar,
+               int64_t nequ, int64_t ncon, int ordering, const int64_t* user_perm, int device,
+               b2_handle** out);
+
+/* try_to_factorize: upload vals (nnz doubles, COO order), COO->CSC accumulate, numeric LDL^T
+ * without pivoting, inertia reduction on the device.  npos = #{d > eig_tol},
+ * nzero = #{|d| <= eig_tol}, nneg = #{d < -eig_tol} (NaN pivots are in none of the three);
+ * breakdown = 1 if an exactly zero pivot was met.  Success in the reference's sense is
+ * npos == nvar && nzero == 0. */
+int b2_factorize(b2_handle* h, const double* vals, double eig_tol, int64_t* npos, int64_t* nzero,
+                 int64_t* nneg, int* breakdown);
+
+/* Retry with new regularisation without re-uploading vals: the rho segment (last nvar COO
+ * entries) becomes rho, and if delta is not NaN the delta segment becomes -delta; the CSC values
+ * are bit-identical to a full b2_factorize of the edited vals.  Requires the canonical COO
+ * layout (b2_analyze detects it; otherwise returns an error and the caller re-uploads). */
+int b2_refactorize_shift(b2_handle* h, double rho, double delta_or_nan, double eig_tol,
+                         int64_t* npos, int64_t* nzero, int64_t* nneg, int* breakdown);
+
+/* solve_ldl!: d_out = (negate ? -1 : +1) * K^{-1} rhs with the last factorization.
+ * refine_steps >= 0 iterative-refinement sweeps with the assembled K; if relres != NULL it
+ * receives ||K x - rhs||_2 / ||rhs||_2 of the returned (un-negated) solution. */
+int b2_solve(b2_handle* h, const double* rhs, double* d_out, int negate, int refine_steps,
+             double* relres);
+
+/* Device-resident variants (inputs/outputs already in HBM); used to time the kernels alone. */
+int b2_factorize_dev(b2_handle* h, const double* d_vals, double eig_tol, int64_t* npos,
+                     int64_t* nzero, int64_t* nneg, int* breakdown);
+int b2_solve_dev(b2_handle* h, const double* d_rhs, double* d_out, int negate, int refine_steps,
+                 double* relres);
+
+/* Pin caller-owned host buffers (vals, rhs, d have stable addresses in the reference:
+ * src/CaNNOLeS.jl:241-243, 276-279) so uploads run at full PCIe speed. */
+int b2_register_host(b2_handle* h, void* ptr, size_t bytes);
+int b2_unregister_host(b2_handle* h, void* ptr);
+
+int b2_stats(const b2_handle* h, b2_stats_t* out);
+/* device milliseconds of the phases of the last call: [0] upload, [1] COO->CSC assembly,
+ * [2] numeric factorization (+ inertia), [3] solve (+ refinement), [4] download */
+int b2_last_timings(const b2_handle* h, double* ms5);
+/* inspection (tests): permutation, assembled CSC values / pattern, pivots in pivot order */
+int b2_get_perm(const b2_handle* h, int64_t* perm0);
+int b2_get_csc(const b2_handle* h, int64_t* colptr0, int64_t* rowval0);
+int b2_get_nzval(b2_handle* h, double* nzval);
+int b2_get_d(b2_handle* h, double* d);
+int b2_set_option(b2_handle* h, const char* key, double value);
+int b2_free(b2_handle* h);
+
+/* ---- batch of independent KKT systems with one pattern (config 5) --------------------- */
+int b2b_analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* cols1, int64_t nvar,
+                int64_t nequ, int64_t ncon, int64_t batch, int ordering, const int64_t* user_perm,
+                int device, b2b_handle** out);
+/* vals: batch x nnz (instance-major).  active == NULL means all instances; otherwise instances
+ * with active[b] == 0 are skipped (their factor and outputs are left untouched). */
+int b2b_factorize(b2b_handle* h, const double* vals, const uint8_t* active, double eig_tol,
+                  int64_t* npos, int64_t* nzero, int64_t* nneg, int32_t* breakdown);
+/* per-instance rho (and delta unless NULL); instances with active[b] == 0 are skipped */
+int b2b_refactorize_shift(b2b_handle* h, const double* rho, const double* delta_or_null,
+                          const uint8_t* active, double eig_tol, int64_t* npos, int64_t* nzero,
+                          int64_t* nneg, int32_t* breakdown);
+/* rhs, d_out: batch x N */
+int b2b_solve(b2b_handle* h, const double* rhs, double* d_out, const uint8_t* active, int negate);
+int b2b_factorize_dev(b2b_handle* h, const double* d_vals, const uint8_t* d_active, double eig_tol,
+                      int64_t* d_counts4 /* batch x 4: pos, zero, neg, breakdown */);
+int b2b_solve_dev(b2b_handle* h, const double* d_rhs, double* d_out, const uint8_t* d_active,
+                  int negate);
+int b2b_stats(const b2b_handle* h, b2_stats_t* out);
+int b2b_free(b2b_handle* h);
+
+/* device utilities used by bench.py / tests (plain cudaMalloc / cudaMemcpy wrappers so that
+ * callers need no CUDA binding of their own) */
+int b2_dev_malloc(void** dptr, size_t bytes);
+int b2_dev_free(void* dptr);
+int b2_dev_upload(void* dptr, const void* hptr, size_t bytes);
+int b2_dev_download(void* hptr, const void* dptr, size_t bytes);
+int b2_dev_sync(void);
+/* FP64 GEMM throughput of this library's own tile kernel and of cuBLAS DGEMM (TFLOP/s), the
+ * roofline denominator for the frontal updates (MEASURED_PEAKS.json has no FP64 entry). */
+int b2_measure_dgemm(int n, int reps, double* tflops_own, double* tflops_cublas);
+int b2_measure_hbm(size_t bytes, int reps, double* gbs_copy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANNOLES_B200_H */
