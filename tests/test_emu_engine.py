@@ -1,0 +1,85 @@
+"""-m "not gpu": the product's kernel sources (cannoles_b200/csrc/*.cu) compiled for the CPU
+emulator in tests/hostsim and checked against the oracle.  This exercises the real symbolic
+analysis, launch plan and kernel code paths without a GPU; it is test infrastructure, the
+product library itself has no CPU path."""
+import os
+
+import numpy as np
+import pytest
+
+from cannoles_b200.models import MGH01CON, ExtRosenbrockLinEq, PoissonParamEst
+from tests import engine_checks as ec
+from tests.problems import EPS, constrained_cases, random_kkt
+
+
+@pytest.fixture()
+def ctor(emu_lib):
+    return ec.backend(emu_lib, pin=False)
+
+
+@pytest.mark.parametrize("ordering", [0, 1, 3])
+def test_small_front_path(ctor, oracle_cls, ordering, monkeypatch):
+    monkeypatch.setenv("B2_SMALL_MAX_M", "128")
+    N, r, c, v = random_kkt(40, 50, 12, 0.1, 21)
+    ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 40, 50, 12, ordering=ordering)
+
+
+@pytest.mark.parametrize("ordering", [0, 1])
+def test_tiled_front_path(ctor, oracle_cls, ordering, monkeypatch):
+    monkeypatch.setenv("B2_SMALL_MAX_M", "8")     # force every front of order > 8 onto the tiled path
+    N, r, c, v = random_kkt(50, 60, 15, 0.3, 22)
+    B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 50, 60, 15, ordering=ordering)
+    assert B.stats()["n_large"] > 0
+
+
+def test_golden_vectors(ctor):
+    for name in ("mgh01con_first_kkt", "random_kkt_0", "random_kkt_1"):
+        ec.check_golden(ctor, name)
+
+
+def test_zero_pivot_is_reported_not_raised(ctor, oracle_cls):
+    """MGH01CON's first KKT matrix in natural order: d = [88, 0, ...] -> False, never an exception."""
+    rows = np.array([1, 1, 2, 2, 3, 4, 4, 5, 3, 4, 5, 1, 2], dtype=np.int64)
+    cols = np.array([1, 1, 1, 2, 1, 1, 2, 1, 3, 4, 5, 1, 2], dtype=np.int64)
+    vals = np.array([88., 0, 0, 0, -1, 24, 10, 1, -1, -1, -0.1, 0, 0])
+    B = ctor(5, rows, cols, vals, nvar=2, nequ=2, ncon=1, ordering=1)
+    assert B.try_to_factorize(vals, 2, 2, 1, EPS) is False
+    assert B.last_inertia[3] is True and B.last_inertia[1] >= 1
+    vals[-2:] = EPS ** (1 / 3)                    # the rho_0 retry of newton_system!
+    assert B.try_to_factorize(vals, 2, 2, 1, EPS) is True
+    assert B.n_shift == 1
+
+
+def test_shift_retry_is_bit_identical(ctor, oracle_cls):
+    N, r, c, v = random_kkt(30, 35, 9, 0.15, 23)
+    ec.check_shift_path(ctor, oracle_cls, N, r, c, v, 30, 35, 9, rho=6.0554544523933395e-06)
+
+
+def test_malformed_input_rejected(ctor):
+    from cannoles_b200.linsolve import B200Error
+    rows = np.array([1, 1], dtype=np.int64)
+    cols = np.array([1, 2], dtype=np.int64)      # strictly upper entry
+    with pytest.raises(B200Error, match="upper"):
+        ctor(2, rows, cols, np.ones(2), nvar=2, nequ=0, ncon=0)
+    with pytest.raises(B200Error, match="range"):
+        ctor(2, np.array([3, 1], dtype=np.int64), np.array([1, 1], dtype=np.int64), np.ones(2), nvar=2, nequ=0, ncon=0)
+
+
+def test_config_slices(ctor, oracle_cls):
+    """Small instances of configs C2 and C4 through the first Newton system."""
+    from scripts.gpu_check import first_system
+    for nls, method in ((ExtRosenbrockLinEq(60), "Newton_noFHess"), (PoissonParamEst(6), "Newton")):
+        import functools
+        s, rhs = first_system(nls, method, functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon))
+        ec.check_against_oracle(ctor, oracle_cls, s.LDLT.N, s.rows, s.cols, s.vals, nls.nvar, nls.nequ, nls.ncon)
+
+
+def test_cannoles_loop_same_iterations_as_oracle(ctor):
+    """Iteration count, nfact, nlinsolve and the final point equal the oracle's on the same order."""
+    nls = MGH01CON()
+    stb, sto = ec.run_cannoles_both(nls, ctor)
+    ec.assert_same_run(stb, sto)
+    for nls, xf in constrained_cases()[:2]:
+        stb, sto = ec.run_cannoles_both(nls, ctor)
+        ec.assert_same_run(stb, sto)
+        assert np.allclose(stb.solution, xf, atol=1e-4)

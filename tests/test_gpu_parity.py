@@ -1,0 +1,132 @@
+"""-m gpu: the CUDA path (libcannoles_b200.so through the C ABI) against the oracle on the same
+seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full sizes --
+through size-independent properties (expected inertia, residual, determinism, linearity)."""
+import functools
+
+import numpy as np
+import pytest
+
+from cannoles_b200.models import MGH01CON, ExtRosenbrockLinEq, PoissonParamEst
+from tests import engine_checks as ec
+from tests.problems import EPS, constrained_cases, hs6, random_kkt, unconstrained_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def ctor(gpu_lib):
+    assert gpu_lib.b2_device_count() > 0
+    return ec.backend()
+
+
+def test_library_is_the_cuda_build(gpu_lib):
+    from cannoles_b200 import _capi
+    assert _capi.LIB_PATH.endswith("csrc/libcannoles_b200.so")
+    for name in _capi.EXPORTS:
+        assert hasattr(gpu_lib, name), name
+
+
+def test_golden_vectors(ctor):
+    for name in ("mgh01con_first_kkt", "random_kkt_0", "random_kkt_1", "random_kkt_2"):
+        ec.check_golden(ctor, name)
+
+
+@pytest.mark.parametrize("ordering", [0, 1, 3])
+@pytest.mark.parametrize("seed", [31, 32])
+def test_random_kkt_against_oracle(ctor, oracle_cls, ordering, seed):
+    nv, ne, nc = 300, 400, 80
+    N, r, c, v = random_kkt(nv, ne, nc, 0.02, seed)
+    ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=ordering)
+
+
+def test_dense_front_tiled_path_against_oracle(ctor, oracle_cls):
+    """One dense 700-order front: five+ pivot blocks, 11 x 11 update tiles."""
+    nv, ne, nc = 250, 350, 100
+    N, r, c, v = random_kkt(nv, ne, nc, 0.6, 33)
+    B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=1)
+    assert B.stats()["n_large"] >= 1 and B.stats()["max_front"] >= 600
+
+
+def test_empty_blocks_and_tiny_systems(ctor, oracle_cls):
+    """ncon = 0 (unconstrained: no delta segment) and a 1 x 1 system."""
+    N, r, c, v = random_kkt(12, 20, 0, 0.3, 34)
+    ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 12, 20, 0)
+    one = np.array([1], dtype=np.int64)
+    ec.check_against_oracle(ctor, oracle_cls, 1, one, one, np.array([2.0]), 1, 0, 0)
+
+
+def test_zero_pivot_and_wrong_inertia_return_false(ctor, oracle_cls):
+    rows = np.array([1, 1, 2, 2, 3, 4, 4, 5, 3, 4, 5, 1, 2], dtype=np.int64)
+    cols = np.array([1, 1, 1, 2, 1, 1, 2, 1, 3, 4, 5, 1, 2], dtype=np.int64)
+    vals = np.array([88., 0, 0, 0, -1, 24, 10, 1, -1, -1, -0.1, 0, 0])
+    B = ctor(5, rows, cols, vals, nvar=2, nequ=2, ncon=1, ordering=1)
+    assert B.try_to_factorize(vals, 2, 2, 1, EPS) is False and B.last_inertia[3] is True
+    # indefinite (1,1) block, no zero pivot: inertia (1, 0, 1) instead of (2, 0, 0)
+    r2 = np.array([1, 2, 1, 2], dtype=np.int64)
+    v2 = np.array([1.0, -3.0, 0.0, 0.0])
+    C = ctor(2, r2, r2, v2, nvar=2, nequ=0, ncon=0)
+    assert C.try_to_factorize(v2, 2, 0, 0, EPS) is False
+    assert C.last_inertia == (1, 0, 1, False)
+    v2[2:] = 5.0                                   # rho = 5 makes it positive definite
+    assert C.try_to_factorize(v2, 2, 0, 0, EPS) is True and C.n_shift == 1
+
+
+def test_shift_retry_is_bit_identical(ctor, oracle_cls):
+    N, r, c, v = random_kkt(200, 260, 50, 0.03, 35)
+    ec.check_shift_path(ctor, oracle_cls, N, r, c, v, 200, 260, 50, rho=6.0554544523933395e-06)
+
+
+def test_config_slices_against_oracle(ctor, oracle_cls):
+    from scripts.gpu_check import first_system
+    for nls, method in ((ExtRosenbrockLinEq(20_000), "Newton_noFHess"), (PoissonParamEst(96), "Newton")):
+        s, rhs = first_system(nls, method, functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon))
+        ec.check_against_oracle(ctor, oracle_cls, s.LDLT.N, s.rows, s.cols, s.vals, nls.nvar, nls.nequ,
+                                nls.ncon, same_perm_tol=1e-8)
+
+
+def test_reference_known_answers_through_the_gpu_backend(ctor):
+    """reference/test/runtests.jl:65-100 with linsolve = b200; and the same iteration counts,
+    nfact, nlinsolve and final point as the oracle on the same elimination order."""
+    for nls, xf in unconstrained_cases() + constrained_cases():
+        stb, sto = ec.run_cannoles_both(nls, ctor)
+        assert np.allclose(stb.solution, xf, atol=1e-4)
+        ec.assert_same_run(stb, sto)
+    stb, sto = ec.run_cannoles_both(MGH01CON(), ctor)
+    ec.assert_same_run(stb, sto)
+    stb, sto = ec.run_cannoles_both(hs6(), ctor)
+    assert stb.status == "first_order" and np.allclose(stb.solution, [1, 1], atol=1e-6)
+    ec.assert_same_run(stb, sto)
+
+
+def test_cannoles_on_a_config_slice_matches_oracle(ctor):
+    nls = PoissonParamEst(24)
+    stb, sto = ec.run_cannoles_both(nls, ctor, max_time=600.0)
+    ec.assert_same_run(stb, sto)
+    nls = ExtRosenbrockLinEq(2000)
+    stb, sto = ec.run_cannoles_both(nls, ctor, method="Newton_noFHess", max_time=600.0)
+    ec.assert_same_run(stb, sto)
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c4"])
+def test_full_size_properties(ctor, cfg):
+    """BASELINE.json full sizes: expected inertia (nvar, 0, nequ+ncon), residual <= 1e-12,
+    run-to-run determinism of the pivots, linearity of the solve."""
+    from scripts.gpu_check import first_system
+    nls, method = ((ExtRosenbrockLinEq(100_000), "Newton_noFHess") if cfg == "c2"
+                   else (PoissonParamEst(512), "Newton"))
+    order = 0 if cfg == "c2" else 3
+    s, rhs = first_system(nls, method, functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon,
+                                                         ordering=order, shift_retries=False))
+    B, N = s.LDLT, s.LDLT.N
+    assert B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    assert B.last_inertia == (nls.nvar, 0, nls.nequ + nls.ncon, False)
+    d1 = B.factor.d
+    assert B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    assert np.array_equal(d1, B.factor.d)                       # deterministic, no atomics on values
+    x1, x2, x3 = np.zeros(N), np.zeros(N), np.zeros(N)
+    b2 = np.random.default_rng(9).standard_normal(N)
+    B.solve_ldl(rhs, x1)
+    assert B.last_relres <= ec.RESID_TOL
+    B.solve_ldl(b2, x2)
+    B.solve_ldl(2.5 * rhs + b2, x3)
+    assert np.linalg.norm(x3 - (2.5 * x1 + x2)) <= 1e-9 * np.linalg.norm(x3)
