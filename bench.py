@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- KKT LDL^T factor+solve throughput of the B200 `linsolve` backend.
+
+A *step* is the linear algebra of ONE Newton system of CaNNOLeS (reference/src/CaNNOLeS.jl
+:1008-1052 with no inertia retry): `try_to_factorize` (COO->CSC accumulate, numeric LDL^T,
+inertia counts) followed by `solve_ldl!`, on the KKT matrix of the named synthetic config at a
+fixed iterate.  Default workload: C4 of BASELINE.json (2-D Poisson-constrained parameter
+estimation on a 512^2 grid, N = 1 310 720 unknowns) -- the ~10^6-unknown system the north-star
+target is quoted on.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3] [--size S]
+  python bench.py --impl reference ...     # the reference's CPU path (restated; see below)
+
+  value  factor+solve per second, whole job, inputs resident in HBM (b2_factorize_dev +
+         b2_solve_dev), CUDA events on the engine's own stream, max over ranks
+  e2e    the same through the reference-facing interface (B200Struct.try_to_factorize /
+         solve_ldl) with pinned HOST buffers: H2D of vals and rhs, D2H of d and the inertia
+         counts inside the timed region
+  N > 1  one KKT system does not shard: every rank factors its own replica
+         ("weak" scaling, no data-path collective); the C5 batch of independent instances is
+         partitioned across ranks and reported in the "batched" sub-object.
+
+`--impl reference`: Julia is not available offline, so the reference arm is the CPU
+restatement of `cannoles(...; linsolve=:ldlfactorizations)`'s factor/solve path
+(oracle/ldl_oracle.c: AMD + up-looking LDL^T, single-threaded like LDLFactorizations.jl).
+"""
+from __future__ import annotations
+
+import argparse
+import functools
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+EPS = 2.0 ** -52
+METRIC = "kkt_factor_solve_per_s"
+UNIT = "KKT factor+solve/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+# ------------------------------------------------------------------------------------------
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0, period=0.2):
+        self.gpu, self.period = gpu_index, period
+        self.samples, self._stop, self._th = [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); smax.append(float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return {"hbm_gbs": FALLBACK_HBM_GBS}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+def build_workload(args, ctor):
+    from cannoles_b200.workloads import first_system, make_config
+    nls, method, desc = make_config(args.workload, args.size)
+    s, rhs = first_system(nls, method, ctor)
+    return nls, method, desc, s, rhs
+
+
+def config_dict(args, desc, st, extra=None):
+    cfg = {"workload": f"{args.workload}: {desc}", "N": int(st["N"]), "nnz_coo": int(st["nnz"]),
+           "nnzA": int(st["nnzA"]), "nnzL": int(st["nnzL"]), "flops_factor": float(st["flops"]),
+           "l2_policy": ("factor panels + contribution blocks = %.0f MB per step, %s the 126 MB L2; no flush"
+                         % (8e-6 * (st["nnzL_store"] + st["cb_store"]),
+                            "larger than" if 8e-6 * (st["nnzL_store"] + st["cb_store"]) > 126 else
+                            "NOT larger than (timing not L2-cold)")),
+           "hessian_mode": None}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU factor/solve path (restated), rank 0 only."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import LDLFactStruct
+    ncores = os.cpu_count() or 1
+    ctor = functools.partial(LDLFactStruct)          # AMD ordering, as ldl_analyze does
+    nls, method, desc, s, rhs = build_workload(args, ctor)
+    O = s.LDLT
+    # one probe repetition sizes the bounded sample
+    t_probe, t3, ok, _ = O.time_factor_solve(s.vals, rhs, nls.nvar, EPS, reps=1)
+    budget = 240.0
+    K = max(1, min(args.steps, int(budget / max(t_probe, 1e-9))))
+    W = min(args.warmup, 1) if t_probe > 5 else args.warmup
+    for _ in range(max(0, W - 1)):               # the probe already was one warm-up
+        O.time_factor_solve(s.vals, rhs, nls.nvar, EPS, reps=1)
+    t0 = time.perf_counter()
+    tt, t3, ok, d = O.time_factor_solve(s.vals, rhs, nls.nvar, EPS, reps=K)
+    wall = time.perf_counter() - t0
+    per = wall / K
+    st = {"N": O.N, "nnz": len(s.vals), "nnzA": O.nnzA, "nnzL": O.nnzL, "flops": O.flops,
+          "nnzL_store": O.nnzL, "cb_store": 0}
+    sample = (f"{K} x full factor+solve of the same KKT system (requested steps={args.steps}; "
+              f"capped so the run ends within ~{budget:.0f} s), AMD ordering, 1 thread "
+              f"(LDLFactorizations.jl is single-threaded); host has {ncores} cores")
+    val = 1.0 / per
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, desc, st, {"hessian_mode": method, "ordering": "amd"}),
+            "phase_ms": {"assemble": t3[0] * 1e3, "factor": t3[1] * 1e3, "solve": t3[2] * 1e3},
+            "inertia_ok": bool(ok),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "restated reference (Julia not available offline); MA57 excluded"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import ctypes as C
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cannoles_b200 import _capi
+    from cannoles_b200.linsolve import B200Struct
+    lib = _capi.load()
+    if lib.b2_device_count() <= 0:
+        raise RuntimeError("bench.py needs a CUDA device: the B200 backend has no CPU fallback")
+    ordering = {"nd": 0, "natural": 1, "amd": 3}[args.ordering]
+    nls_dims = {}
+
+    def ctor(N, rows, cols, vals):
+        return B200Struct(N, rows, cols, vals, ordering=ordering, device=local,
+                          refine_steps=args.refine, shift_retries=False, **nls_dims)
+
+    from cannoles_b200.workloads import make_config, first_system
+    nls, method, desc = make_config(args.workload, args.size)
+    nls_dims.update(nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon)
+    s, rhs = first_system(nls, method, ctor)
+    B = s.LDLT
+    N, nnz = B.N, len(s.vals)
+    st = B.stats()
+    d_host = np.zeros(N)
+    B.register_host(rhs)
+    B.register_host(d_host)
+    h = B._h
+    vp = C.c_void_p
+
+    def chk(rc):
+        if rc != 0:
+            raise RuntimeError(_capi.last_error(lib))
+
+    # device-resident inputs for the `value` leg
+    dv, dr, do = vp(), vp(), vp()
+    chk(lib.b2_dev_malloc(C.byref(dv), nnz * 8))
+    chk(lib.b2_dev_malloc(C.byref(dr), N * 8))
+    chk(lib.b2_dev_malloc(C.byref(do), N * 8))
+    chk(lib.b2_dev_upload(dv, s.vals.ctypes.data_as(vp), nnz * 8))
+    chk(lib.b2_dev_upload(dr, rhs.ctypes.data_as(vp), N * 8))
+    npos, nzero, nneg, brk = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+    rr = C.c_double()
+    ms5 = np.zeros(5)
+
+    def step_dev():
+        chk(lib.b2_factorize_dev(h, dv, EPS, C.byref(npos), C.byref(nzero), C.byref(nneg), C.byref(brk)))
+        chk(lib.b2_last_timings(h, ms5.ctypes.data_as(_capi.pd)))
+        t_asm, t_fac = ms5[1], ms5[2]
+        chk(lib.b2_solve_dev(h, dr, do, 1, args.refine, None))
+        chk(lib.b2_last_timings(h, ms5.ctypes.data_as(_capi.pd)))
+        return t_asm, t_fac, ms5[3]
+
+    def step_host():
+        ok = B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+        B.solve_ldl(rhs, d_host)
+        return ok
+
+    def barrier():
+        chk(lib.b2_dev_sync())
+        if dist is not None:
+            dist.barrier()
+        chk(lib.b2_dev_sync())
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (also captures the CUDA graphs) and correctness gate ----------------------
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    ok = step_host()
+    inertia = B.last_inertia
+    relres = B.last_relres
+    expected = (nls.nvar, 0, nls.nequ + nls.ncon, False)
+    if not ok or inertia != expected:
+        raise RuntimeError(f"wrong inertia {inertia}, expected {expected}")
+    for _ in range(2):
+        step_host()
+
+    # ---- timed region 1: device-resident ---------------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    chk(lib.b2_timer_start(h))
+    t0 = time.perf_counter()
+    ph = np.zeros(3)
+    for _ in range(args.steps):
+        ph += step_dev()
+    tms = C.c_double()
+    chk(lib.b2_timer_stop(h, C.byref(tms)))
+    barrier()
+    wall_dev = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = max_over_ranks(tms.value)
+    ph = np.maximum(ph / args.steps, 1e-9)   # (1e-9 only ever bites on the CPU emulator used to debug this script)
+    dev_ms = max(dev_ms, 1e-9)
+
+    # ---- timed region 2: end to end through the reference-facing interface -----------------
+    barrier()
+    chk(lib.b2_timer_start(h))
+    for _ in range(args.steps):
+        step_host()
+    chk(lib.b2_timer_stop(h, C.byref(tms)))
+    barrier()
+    e2e_ms = max(max_over_ranks(tms.value), 1e-9)
+    relres = B.last_relres
+
+    # ---- roofline --------------------------------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
+    own, cub = C.c_double(), C.c_double()
+    fp64_peak = None
+    if rank == 0 and hasattr(lib, "b2_measure_dgemm") and lib.b2_measure_dgemm(4096, 5, C.byref(own), C.byref(cub)) == 0:
+        fp64_peak = cub.value
+    nnzA, nnzL = st["nnzA"], st["nnzL"]
+    bytes_asm = 8 * nnz + 4 * nnz + 4 * nnzA + 8 * nnzA
+    bytes_fact = 8 * (nnzA + nnzL + N)
+    bytes_solve = (1 + args.refine) * (2 * 8 * nnzL + 8 * 3 * N) + args.refine * (12 * nnzA + 16 * N)
+    fact_tflops = st["flops"] / (ph[1] * 1e-3) / 1e12
+    roof = {"kernel": "numeric LDL^T factorization (one CUDA-graph launch: all fronts, all levels)",
+            "bound": "tensor", "achieved": fact_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": (fact_tflops / fp64_peak) if fp64_peak else None, "traffic": None,
+            "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+            "algorithmic_flops_per_launch": st["flops"], "ms_per_launch": ph[1],
+            "hbm_view": {"achieved": bytes_fact / (ph[1] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": bytes_fact / (ph[1] * 1e-3) / 1e9 / hbm_peak}}
+    phases = {
+        "assemble": {"bound": "hbm", "ms": ph[0], "achieved": bytes_asm / (ph[0] * 1e-3) / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": bytes_asm / (ph[0] * 1e-3) / 1e9 / hbm_peak},
+        "solve": {"bound": "hbm", "ms": ph[2], "achieved": bytes_solve / (ph[2] * 1e-3) / 1e9,
+                  "peak": hbm_peak, "unit": "GB/s", "frac": bytes_solve / (ph[2] * 1e-3) / 1e9 / hbm_peak},
+        "peak_source": peak_src}
+
+    value = world * args.steps / (dev_ms * 1e-3)
+    e2e_val = world * args.steps / (e2e_ms * 1e-3)
+    launches_step = int(st["launches_factor"] + st["launches_solve"] * (1 + args.refine))
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample ------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import LDLFactStruct
+        O = LDLFactStruct(N, s.rows, s.cols, s.vals)
+        t, t3, okc, _ = O.time_factor_solve(s.vals, rhs, nls.nvar, EPS, reps=1)
+        cpu = {"value": 1.0 / t, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "1 x full factor+solve of the same KKT system (AMD ordering, up-looking "
+                         "LDL^T restated from LDLFactorizations.jl, 1 thread; host has %d cores)"
+                         % (os.cpu_count() or 1),
+               "phase_ms": {"assemble": t3[0] * 1e3, "factor": t3[1] * 1e3, "solve": t3[2] * 1e3},
+               "inertia_ok": bool(okc)}
+
+    batched = None
+    if not args.no_batched:
+        try:
+            from cannoles_b200.batched import bench_batched
+        except ImportError:
+            bench_batched = None
+        if bench_batched is not None:
+            batched = bench_batched(args, rank, world, local, dist)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": config_dict(args, desc, st, {
+                    "hessian_mode": method, "ordering": args.ordering, "refine_steps": args.refine,
+                    "nsuper": int(st["nsuper"]), "nlevels": int(st["nlevels"]),
+                    "max_front": int(st["max_front"]), "parallelism": f"replicas x{world}"}),
+                "phase_ms": {"assemble": ph[0], "factor": ph[1], "solve": ph[2]},
+                "wall_ms_per_step": wall_dev / args.steps * 1e3,
+                "inertia": list(inertia[:3]), "relres": relres,
+                "roofline": roof, "roofline_phases": phases, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                        "h2d_bytes_per_step": 8 * nnz + 8 * N, "d2h_bytes_per_step": 8 * N + 40},
+                "gpu_launches": launches_step * args.steps, "clocks": clocks,
+                "analyze_s": {"order": st["t_order"], "symbolic": st["t_symbolic"], "plan": st["t_plan"]}}
+        if batched is not None:
+            line["batched"] = batched
+        print(json.dumps(line), flush=True)
+    for p in (dv, dr, do):
+        lib.b2_dev_free(p)
+    B.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4"])
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--ordering", default="nd", choices=["nd", "amd", "natural"])
+    ap.add_argument("--refine", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-batched", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,6 +142,22 @@ int b2_last_timings(const b2_handle* h, double* ms5) {
   return 0;
 }
 
+int b2_timer_start(b2_handle* h) {
+  if (!h) return fail("b2_timer_start: NULL handle");
+  if (cudaEventRecord(h->eng.tev[0], h->eng.stream) != cudaSuccess) return fail("b2_timer_start: record failed");
+  return 0;
+}
+
+int b2_timer_stop(b2_handle* h, double* ms) {
+  if (!h || !ms) return fail("b2_timer_stop: NULL argument");
+  if (cudaEventRecord(h->eng.tev[1], h->eng.stream) != cudaSuccess) return fail("b2_timer_stop: record failed");
+  if (cudaEventSynchronize(h->eng.tev[1]) != cudaSuccess) return fail("b2_timer_stop: sync failed");
+  float f = 0;
+  if (cudaEventElapsedTime(&f, h->eng.tev[0], h->eng.tev[1]) != cudaSuccess) return fail("b2_timer_stop: elapsed failed");
+  *ms = f;
+  return 0;
+}
+
 int b2_get_perm(const b2_handle* h, int64_t* perm0) {
   if (!h || !perm0) return fail("b2_get_perm: NULL argument");
   for (int64_t k = 0; k < h->eng.sym.N; k++) perm0[k] = h->eng.sym.perm[k];

@@ -148,6 +148,7 @@ int Engine::init(int dev) {
   B2_CUDA_OK(cudaSetDevice(dev));
   B2_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto& e : ev) B2_CUDA_OK(cudaEventCreate(&e));
+  for (auto& e : tev) B2_CUDA_OK(cudaEventCreate(&e));
   const Symbolic& S = sym;
   if ((size_t)(S.max_front + NB) * sizeof(double) > 200 * 1024) {
     snprintf(g_last_error, sizeof(g_last_error), "front of order %d exceeds the solve kernels' shared memory", S.max_front);
@@ -221,6 +222,7 @@ void Engine::destroy() {
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
+  for (auto& e : tev) if (e) cudaEventDestroy(e);
   if (stream) cudaStreamDestroy(stream);
 }
 

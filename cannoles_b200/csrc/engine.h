@@ -64,6 +64,7 @@ struct Engine {
   bool have_vals = false, factored = false;
   double last_ms[5] = {0, 0, 0, 0, 0};
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t tev[2] = {nullptr, nullptr};  // b2_timer_start / b2_timer_stop
 #ifndef B2_EMULATE
   cudaGraphExec_t g_fact = nullptr, g_fwdbwd = nullptr;
 #endif

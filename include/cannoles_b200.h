@@ -107,6 +107,10 @@ int b2_stats(const b2_handle* h, b2_stats_t* out);
 /* device milliseconds of the phases of the last call: [0] upload, [1] COO->CSC assembly,
  * [2] numeric factorization (+ inertia), [3] solve (+ refinement), [4] download */
 int b2_last_timings(const b2_handle* h, double* ms5);
+/* CUDA events on the handle's own stream (bench.py times K steps between the two; a
+ * torch.cuda.Event would only see torch's current stream) */
+int b2_timer_start(b2_handle* h);
+int b2_timer_stop(b2_handle* h, double* ms);
 /* inspection (tests): permutation, assembled CSC values / pattern, pivots in pivot order */
 int b2_get_perm(const b2_handle* h, int64_t* perm0);
 int b2_get_csc(const b2_handle* h, int64_t* colptr0, int64_t* rowval0);

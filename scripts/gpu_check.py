@@ -10,7 +10,6 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cannoles_b200.linsolve import B200Struct  # noqa: E402
 from cannoles_b200.models import ExtRosenbrockLinEq, PoissonParamEst  # noqa: E402
-from cannoles_b200.solver import CaNNOLeSSolver, prepare_newton_system  # noqa: E402
 
 EPS = 2.0 ** -52
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
@@ -25,21 +24,7 @@ def emit(**kw):
     log.flush()
 
 
-def first_system(nls, method, ctor):
-    """Solver + the vals / rhs of the first Newton system (rho = 0, delta = 0.1-ish)."""
-    s = CaNNOLeSSolver(nls, linsolve=ctor, method=method)
-    x = nls.x0.copy()
-    Fx = np.zeros(nls.nequ)
-    nls.residual(x, Fx)
-    nls.jac_coord_residual(x, s.Jx_vals)
-    cx = np.zeros(nls.ncon)
-    nls.cons(x, cx)
-    nls.jac_coord(x, s.Jcx_vals)
-    lam = np.ones(nls.ncon)
-    prepare_newton_system(s, nls, x, lam, Fx, 0.1)
-    rng = np.random.default_rng(7)
-    rhs = rng.standard_normal(nls.nvar + nls.nequ + nls.ncon)
-    return s, rhs
+from cannoles_b200.workloads import first_system  # noqa: E402,F401
 
 
 def run(nls, method, ordering, tag, parity, reps=5):
