@@ -37,7 +37,8 @@ EXPORTS = [
     "b2_unregister_host", "b2_stats", "b2_last_timings", "b2_timer_start", "b2_timer_stop", "b2_get_perm", "b2_get_csc",
     "b2_get_nzval", "b2_get_d", "b2_set_option", "b2_free",
     "b2b_analyze", "b2b_factorize", "b2b_refactorize_shift", "b2b_solve", "b2b_factorize_dev",
-    "b2b_solve_dev", "b2b_stats", "b2b_free",
+    "b2b_solve_dev", "b2b_factor_solve", "b2b_factor_solve_dev", "b2b_stats", "b2b_last_ms",
+    "b2b_timer_start", "b2b_timer_stop", "b2b_get_perm", "b2b_get_d", "b2b_free",
     "b2_dev_malloc", "b2_dev_free", "b2_dev_upload", "b2_dev_download", "b2_dev_sync",
     "b2_measure_dgemm", "b2_measure_hbm",
 ]
@@ -75,7 +76,14 @@ def bind_library(path: str):
         lib.b2b_solve.argtypes = [vp, pd, pd, pu8, C.c_int]
         lib.b2b_factorize_dev.argtypes = [vp, vp, vp, C.c_double, vp]
         lib.b2b_solve_dev.argtypes = [vp, vp, vp, vp, C.c_int]
+        lib.b2b_factor_solve.argtypes = [vp, pd, pd, pd, pu8, C.c_double, C.c_int, p64, p64, p64, p32]
+        lib.b2b_factor_solve_dev.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_int, C.c_int, vp]
         lib.b2b_stats.argtypes = [vp, C.POINTER(Stats)]
+        lib.b2b_last_ms.argtypes = [vp, pd]
+        lib.b2b_timer_start.argtypes = [vp]
+        lib.b2b_timer_stop.argtypes = [vp, pd]
+        lib.b2b_get_perm.argtypes = [vp, p64]
+        lib.b2b_get_d.argtypes = [vp, C.c_int64, pd]
         lib.b2b_free.argtypes = [vp]
     if hasattr(lib, "b2_dev_malloc"):
         lib.b2_dev_malloc.argtypes = [C.POINTER(vp), C.c_size_t]

@@ -35,9 +35,19 @@ def make_config(name: str, size: int | None = None):
     raise ValueError(f"unknown config {name!r}")
 
 
-def first_system(nls, method, ctor, delta=0.1, seed=7):
-    """Solver + the vals / rhs of the first Newton system (rho = 0, given delta)."""
-    s = CaNNOLeSSolver(nls, linsolve=ctor, method=method)
+class _NoBackend:
+    """Placeholder ``linsolve`` for building only the COO structure of a solver."""
+
+    def __init__(self, N, rows, cols, vals):
+        self.vals = vals
+
+    def get_vals(self):
+        return self.vals
+
+
+def fill_first_system(s, nls, delta=0.1, seed=7):
+    """Fill ``s.vals`` with the first Newton system of ``nls`` (same structure as the model ``s``
+    was built for) and return the right-hand side."""
     x = nls.x0.copy()
     Fx = np.zeros(nls.nequ)
     nls.residual(x, Fx)
@@ -48,5 +58,26 @@ def first_system(nls, method, ctor, delta=0.1, seed=7):
     lam = np.ones(nls.ncon)
     prepare_newton_system(s, nls, x, lam, Fx, delta)
     rng = np.random.default_rng(seed)
-    rhs = rng.standard_normal(nls.nvar + nls.nequ + nls.ncon)
+    return rng.standard_normal(nls.nvar + nls.nequ + nls.ncon)
+
+
+def first_system(nls, method, ctor, delta=0.1, seed=7):
+    """Solver + the vals / rhs of the first Newton system (rho = 0, given delta)."""
+    s = CaNNOLeSSolver(nls, linsolve=ctor, method=method)
+    rhs = fill_first_system(s, nls, delta, seed)
     return s, rhs
+
+
+def dense_batch_systems(instances, delta=0.1):
+    """Config 5: the first Newton systems of the given instances of ``DenseBatchNLS`` (per-instance
+    seed 1000 + i).  Returns (structure solver, vals[B, nnz], rhs[B, N]); the COO pattern
+    (``s.rows``, ``s.cols``) is shared by all instances."""
+    instances = list(instances)
+    s = CaNNOLeSSolver(DenseBatchNLS(instances[0] if instances else 0), linsolve=_NoBackend, method="Newton")
+    N = s.nvar + s.nequ + s.ncon
+    vals = np.empty((len(instances), len(s.vals)))
+    rhs = np.empty((len(instances), N))
+    for b, i in enumerate(instances):
+        rhs[b] = fill_first_system(s, DenseBatchNLS(i), delta, seed=7 + i)
+        vals[b] = s.vals
+    return s, vals, rhs

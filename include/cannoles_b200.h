@@ -137,7 +137,23 @@ int b2b_factorize_dev(b2b_handle* h, const double* d_vals, const uint8_t* d_acti
                       int64_t* d_counts4 /* batch x 4: pos, zero, neg, breakdown */);
 int b2b_solve_dev(b2b_handle* h, const double* d_rhs, double* d_out, const uint8_t* d_active,
                   int negate);
+/* Fused verb: factorize every active instance and, where the inertia is the expected one
+ * (npos == nvar && nzero == 0), solve right away from the factor still resident in shared
+ * memory (d_out = (negate ? -1 : +1) K^{-1} rhs).  Instances whose inertia is wrong leave their
+ * slice of d_out untouched; the caller retries them with b2b_refactorize_shift + b2b_solve, as
+ * newton_system! does one system at a time (src/CaNNOLeS.jl:1029-1049). */
+int b2b_factor_solve(b2b_handle* h, const double* vals, const double* rhs, double* d_out,
+                     const uint8_t* active, double eig_tol, int negate, int64_t* npos, int64_t* nzero,
+                     int64_t* nneg, int32_t* breakdown);
+int b2b_factor_solve_dev(b2b_handle* h, const double* d_vals, const double* d_rhs, double* d_out,
+                         const uint8_t* d_active, double eig_tol, int negate, int store_factor,
+                         int64_t* d_counts4);
 int b2b_stats(const b2b_handle* h, b2_stats_t* out);
+int b2b_last_ms(const b2b_handle* h, double* ms);    /* device time of the last kernel launch */
+int b2b_timer_start(b2b_handle* h);
+int b2b_timer_stop(b2b_handle* h, double* ms);
+int b2b_get_perm(const b2b_handle* h, int64_t* perm0);
+int b2b_get_d(b2b_handle* h, int64_t instance, double* d); /* pivots of one stored factor */
 int b2b_free(b2b_handle* h);
 
 /* device utilities used by bench.py / tests (plain cudaMalloc / cudaMemcpy wrappers so that
