@@ -13,9 +13,6 @@ Multi-GPU: ``partition(batch, rank, world)`` gives the contiguous block of insta
 from __future__ import annotations
 
 import ctypes as C
-import os
-import time
-
 import numpy as np
 
 from . import _capi
@@ -211,126 +208,3 @@ def gather_records(rec: np.ndarray, dist=None, device=None):
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad)
     return np.concatenate([o[:int(s.item())].cpu().numpy() for o, s in zip(outs, sizes)], axis=0)
-
-
-def smoke_batched(batch=6):
-    """A few config-5 instances through the fused kernel, checked against the oracle."""
-    from oracle import LDLFactStruct
-    from .workloads import dense_batch_systems
-    s, vals, rhs = dense_batch_systems(range(batch))
-    nv, ne, nc = s.nvar, s.nequ, s.ncon
-    N = nv + ne + nc
-    Bt = B200BatchStruct(N, s.rows, s.cols, batch, nv, ne, nc)
-    d = np.zeros((batch, N))
-    ok = Bt.factor_solve(vals, rhs, d)
-    assert ok.all(), (Bt.npos, Bt.nzero)
-    O = LDLFactStruct(N, s.rows, s.cols, vals[0].copy(), perm=Bt.perm)
-    for b in range(batch):
-        assert O.try_to_factorize(vals[b], nv, ne, nc, EPS)
-        assert (Bt.npos[b], Bt.nzero[b], Bt.nneg[b]) == O.inertia(EPS)
-        do = np.zeros(N)
-        O.solve_ldl(rhs[b], do)
-        assert np.linalg.norm(d[b] - do) <= 1e-9 * np.linalg.norm(do)
-        r = O.matvec(d[b]) + rhs[b]
-        assert np.linalg.norm(r) <= 1e-12 * np.linalg.norm(rhs[b]), np.linalg.norm(r) / np.linalg.norm(rhs[b])
-    print("smoke_batched ok: %d instances, N=%d, kernel %.3f ms" % (batch, N, Bt.last_ms()))
-    Bt.close()
-
-
-def bench_batched(args, rank, world, local, dist, total=None, steps=None):
-    """C5: `total` independent instances partitioned over the ranks; a step = fused
-    factorize + inertia + solve of every instance of the rank (values resident in HBM).
-    Returns the "batched" sub-object of the bench line (rank 0) or None."""
-    from .workloads import dense_batch_systems
-    lib = _capi.load()
-    total = int(total or os.environ.get("B2_BENCH_BATCH", 8192))
-    steps = int(steps or max(3, min(args.steps, 20)))
-    lo, hi = partition(total, rank, world)
-    nb = hi - lo
-    t0 = time.perf_counter()
-    s, vals, rhs = dense_batch_systems(range(lo, hi))
-    t_gen = time.perf_counter() - t0
-    nv, ne, nc = s.nvar, s.nequ, s.ncon
-    N, nnz = nv + ne + nc, vals.shape[1]
-    Bt = B200BatchStruct(N, s.rows, s.cols, nb, nv, ne, nc, device=local)
-    st = Bt.stats()
-    vp = C.c_void_p
-
-    def chk(rc):
-        if rc != 0:
-            raise B200Error(_capi.last_error(lib))
-
-    dv, dr, do, dc = vp(), vp(), vp(), vp()
-    chk(lib.b2_dev_malloc(C.byref(dv), vals.nbytes))
-    chk(lib.b2_dev_malloc(C.byref(dr), rhs.nbytes))
-    chk(lib.b2_dev_malloc(C.byref(do), rhs.nbytes))
-    chk(lib.b2_dev_malloc(C.byref(dc), nb * 32))
-    chk(lib.b2_dev_upload(dv, vals.ctypes.data_as(vp), vals.nbytes))
-    chk(lib.b2_dev_upload(dr, rhs.ctypes.data_as(vp), rhs.nbytes))
-    h = Bt._h
-
-    def sync():
-        chk(lib.b2_dev_sync())
-        if dist is not None:
-            dist.barrier()
-        chk(lib.b2_dev_sync())
-
-    for _ in range(3):
-        chk(lib.b2b_factor_solve_dev(h, dv, dr, do, None, EPS, 1, 0, dc))
-    sync()
-    chk(lib.b2b_timer_start(h))
-    for _ in range(steps):
-        chk(lib.b2b_factor_solve_dev(h, dv, dr, do, None, EPS, 1, 0, dc))
-    ms = C.c_double()
-    chk(lib.b2b_timer_stop(h, C.byref(ms)))
-    sync()
-    dev_ms = ms.value
-    # end to end from pinned-size host arrays through the public verb
-    d = np.zeros((nb, N))
-    ok = Bt.factor_solve(vals, rhs, d)
-    sync()
-    t1 = time.perf_counter()
-    chk(lib.b2b_timer_start(h))
-    e2e_steps = max(2, steps // 4)
-    for _ in range(e2e_steps):
-        ok = Bt.factor_solve(vals, rhs, d)
-    chk(lib.b2b_timer_stop(h, C.byref(ms)))
-    sync()
-    e2e_ms = ms.value
-    e2e_wall = (time.perf_counter() - t1) * 1e3
-    # per-instance record: [ok, npos, nzero, nneg, ||d||]
-    rec = np.stack([ok.astype(np.float64), Bt.npos.astype(np.float64), Bt.nzero.astype(np.float64),
-                    Bt.nneg.astype(np.float64), np.linalg.norm(d, axis=1)], axis=1)
-    if dist is not None:
-        import torch
-        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0].item()), float(t[1].item())
-        allrec = gather_records(rec, dist, device="cuda")
-    else:
-        allrec = rec
-    for p in (dv, dr, do, dc):
-        lib.b2_dev_free(p)
-    Bt.close()
-    if rank != 0:
-        return None
-    flops_inst = st["flops"]
-    out = {"metric": "batched_kkt_factor_solve_per_s", "unit": "instances/s",
-           "value": total * steps / (dev_ms * 1e-3), "ms_per_step": dev_ms / steps,
-           "e2e": {"value": total * e2e_steps / (e2e_ms * 1e-3), "unit": "instances/s",
-                   "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall / e2e_steps,
-                   "h2d_bytes_per_step": int(vals.nbytes + 2 * rhs.nbytes) * world,
-                   "d2h_bytes_per_step": int(rhs.nbytes + nb * 32) * world},
-           "config": {"workload": "c5: %d independent constrained NLS (n=%d, m=%d, %d constraints), "
-                                  "first Newton system of each" % (total, nv, ne, nc),
-                      "N": N, "nnz_coo": nnz, "batch_total": total, "batch_per_rank": nb,
-                      "nnzL": int(st["nnzL"]), "flops_factor_per_instance": flops_inst,
-                      "nsuper": int(st["nsuper"]), "nlevels": int(st["nlevels"])},
-           "steps": steps, "n_gpus": world, "scaling": "strong",
-           "all_ok": bool((allrec[:, 0] == 1).all()), "records_gathered": int(allrec.shape[0]),
-           "roofline": {"bound": "tensor", "unit": "TFLOP/s",
-                        "achieved": flops_inst * (total / world) * steps / (dev_ms * 1e-3) / 1e12,
-                        "note": "per GPU; algorithmic flops sum_j(c_j^2+3c_j) per instance",
-                        "hbm_GBs": (8.0 * nnz + 16.0 * N) * (total / world) * steps / (dev_ms * 1e-3) / 1e9},
-           "generate_s": t_gen}
-    return out
