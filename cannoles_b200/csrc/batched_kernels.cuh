@@ -13,6 +13,7 @@
 // Algorithmic bytes per instance: 8 nnz in (+ 8 N rhs) and 8 N out; flops: sum_j (c_j^2 + 3 c_j).
 #pragma once
 #include "b2_cuda.h"
+#include "mma.cuh"
 
 namespace b2 {
 
@@ -34,29 +35,6 @@ struct BatchPlanDev {
   const int32_t* multi_ptr;  // nmulti+1 into multi_coo
   const int32_t* multi_coo;  // COO indices, ascending inside a slot
 };
-
-// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores.  Fragment layout (PTX mma.m8n8k4.f64):
-// a = A[lane/4][lane%4], b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + {0,1}].
-__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
-#ifdef B2_EMULATE
-  const int lane = threadIdx.x & 31;
-  const int row = lane >> 2, cp = (lane & 3) * 2;
-  double s0 = 0.0, s1 = 0.0;
-  for (int k = 0; k < 4; k++) {
-    const double av = __shfl_sync(0xffffffffu, a, row * 4 + k);
-    const double b0 = __shfl_sync(0xffffffffu, b, cp * 4 + k);
-    const double b1 = __shfl_sync(0xffffffffu, b, (cp + 1) * 4 + k);
-    s0 += av * b0;
-    s1 += av * b1;
-  }
-  c0 += s0;
-  c1 += s1;
-#else
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-#endif
-}
 
 // flags: bit0 = write the packed factor to Lout, bit1 = solve with rhs -> dout (only if the
 // inertia is the expected one), bit2 = negate the solution (solve_ldl!'s sign flip),

@@ -76,7 +76,7 @@ int Engine::build_plan() {
       if (!sol[c].empty()) {
         Launch L; L.kind = LK_FWD; L.cls = c; L.off = (int64_t)items.size();
         L.count = (int)sol[c].size();
-        L.smem = (int)(((size_t)sol_mmax[c] + NB) * sizeof(double));
+        L.smem = (int)(((size_t)sol_mmax[c] + SNB) * sizeof(double));
         items.insert(items.end(), sol[c].begin(), sol[c].end());
         fwd_launches.push_back(L);
         L.kind = LK_BWD;
@@ -87,14 +87,14 @@ int Engine::build_plan() {
     {
       Launch L; L.kind = LK_ASSEMBLE_LARGE; L.off = (int64_t)items.size();
       for (int s : large) {
-        int nblk = (front_m(s) + ASM_COLS - 1) / ASM_COLS;
-        for (int cb = 0; cb < nblk; cb++) { items.push_back(s); items.push_back(cb); L.count++; }
+        int m = front_m(s);
+        int ncb = (m + ASM_COLS - 1) / ASM_COLS, nrb = (m + ASM_ROWS - 1) / ASM_ROWS;
+        for (int cb = 0; cb < ncb; cb++)
+          for (int rb = 0; rb < nrb; rb++) {
+            if ((rb + 1) * ASM_ROWS <= cb * ASM_COLS) continue;   // tile entirely above the diagonal
+            items.push_back(s); items.push_back(cb); items.push_back(rb); L.count++;
+          }
       }
-      fact_launches.push_back(L);
-    }
-    {
-      Launch L; L.kind = LK_DIAG_FACTOR; L.off = (int64_t)items.size(); L.jb = 0;
-      for (int s : large) { items.push_back(s); L.count++; }
       fact_launches.push_back(L);
     }
     int wmax = 0;
@@ -106,7 +106,8 @@ int Engine::build_plan() {
         if (w <= jb) continue;
         int nb = std::min(NB, w - jb);
         int nrows = m - (jb + nb);
-        for (int ch = 0; ch * TRSM_ROWS < nrows; ch++) { items.push_back(s); items.push_back(ch); T.count++; }
+        int nch = std::max(1, (nrows + TRSM_ROWS - 1) / TRSM_ROWS);   // chunk 0 always exists: it owns the diagonal block
+        for (int ch = 0; ch < nch; ch++) { items.push_back(s); items.push_back(ch); T.count++; }
       }
       if (T.count) fact_launches.push_back(T);
       Launch U; U.kind = LK_UPDATE; U.off = (int64_t)items.size(); U.jb = jb; U.mode = 0;
@@ -150,7 +151,7 @@ int Engine::init(int dev) {
   for (auto& e : ev) B2_CUDA_OK(cudaEventCreate(&e));
   for (auto& e : tev) B2_CUDA_OK(cudaEventCreate(&e));
   const Symbolic& S = sym;
-  if ((size_t)(S.max_front + NB) * sizeof(double) > 200 * 1024) {
+  if ((size_t)(S.max_front + SNB) * sizeof(double) > 200 * 1024) {
     snprintf(g_last_error, sizeof(g_last_error), "front of order %d exceeds the solve kernels' shared memory", S.max_front);
     return -1;
   }
@@ -238,9 +239,6 @@ int Engine::run_factor_launches() {
         break;
       case LK_ASSEMBLE_LARGE:
         B2_LAUNCH(k_assemble_large, L.count, 256, 0, stream, plan, it, L.count);
-        break;
-      case LK_DIAG_FACTOR:
-        B2_LAUNCH(k_diag_factor, L.count, 32, 0, stream, plan, it, L.count, L.jb);
         break;
       case LK_TRSM:
         B2_LAUNCH(k_trsm, L.count, TRSM_ROWS, 0, stream, plan, it, L.count, L.jb);

@@ -24,9 +24,13 @@ struct PlanDev {
   int* flags;  // [0] = breakdown (exact zero pivot seen)
 };
 
-constexpr int NB = 32;      // pivot block width of the tiled path
-constexpr int TILE = 64;    // update tile (TILE x TILE per CTA)
+constexpr int NB = 64;        // pivot block width of the tiled path (== TILE: tile (0,0) is the next diagonal block)
+constexpr int TILE = 64;      // update tile (TILE x TILE per CTA)
+constexpr int UPD_KC = 16;    // K-chunk of k_update's shared-memory pipeline
+constexpr int DIAG_LD = 65;   // leading dimension of a diagonal block in shared memory
 constexpr int TRSM_ROWS = 128;
-constexpr int ASM_COLS = 8; // destination columns per CTA in k_assemble_large
+constexpr int ASM_COLS = 8;   // destination tile of k_assemble_large: ASM_ROWS x ASM_COLS
+constexpr int ASM_ROWS = 512;
+constexpr int SNB = 32;       // column block of the solve kernels
 
 }  // namespace b2

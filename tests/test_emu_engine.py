@@ -32,6 +32,14 @@ def test_tiled_front_path(ctor, oracle_cls, ordering, monkeypatch):
     assert B.stats()["n_large"] > 0
 
 
+def test_tiled_path_multi_block_front(ctor, oracle_cls, monkeypatch):
+    """One dense front of order 150 on the tiled path: three pivot blocks (64, 64, 22), DMMA tiles."""
+    monkeypatch.setenv("B2_SMALL_MAX_M", "8")
+    N, r, c, v = random_kkt(60, 70, 20, 0.5, 71)
+    B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 60, 70, 20, ordering=1)
+    assert B.stats()["max_width"] > 128
+
+
 def test_golden_vectors(ctor):
     for name in ("mgh01con_first_kkt", "random_kkt_0", "random_kkt_1"):
         ec.check_golden(ctor, name)
