@@ -223,12 +223,15 @@ def run_b200(args):
     rr = C.c_double()
     ms5 = np.zeros(5)
 
+    sweeps = [1]
+
     def step_dev():
         chk(lib.b2_factorize_dev(h, dv, EPS, C.byref(npos), C.byref(nzero), C.byref(nneg), C.byref(brk)))
         chk(lib.b2_last_timings(h, ms5.ctypes.data_as(_capi.pd)))
         t_asm, t_fac = ms5[1], ms5[2]
         chk(lib.b2_solve_dev(h, dr, do, 1, args.refine, None))
         chk(lib.b2_last_timings(h, ms5.ctypes.data_as(_capi.pd)))
+        sweeps[0] = lib.b2_last_sweeps(h)
         return t_asm, t_fac, ms5[3]
 
     def step_host():
@@ -301,7 +304,9 @@ def run_b200(args):
     nnzA, nnzL = st["nnzA"], st["nnzL"]
     bytes_asm = 8 * nnz + 4 * nnz + 4 * nnzA + 8 * nnzA
     bytes_fact = 8 * (nnzA + nnzL + N)
-    bytes_solve = (1 + args.refine) * (2 * 8 * nnzL + 8 * 3 * N) + args.refine * (12 * nnzA + 16 * N)
+    nsw = sweeps[0]                       # sweeps actually taken (adaptive refinement)
+    nres = min(nsw, args.refine) if args.refine > 0 else 0
+    bytes_solve = nsw * (2 * 8 * nnzL + 8 * 3 * N) + nres * (12 * nnzA + 16 * N)
     fact_tflops = st["flops"] / (ph[1] * 1e-3) / 1e12
     roof = {"kernel": "numeric LDL^T factorization (one CUDA-graph launch: all fronts, all levels)",
             "bound": "tensor", "achieved": fact_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -319,7 +324,7 @@ def run_b200(args):
 
     value = world * args.steps / (dev_ms * 1e-3)
     e2e_val = world * args.steps / (e2e_ms * 1e-3)
-    launches_step = int(st["launches_factor"] + st["launches_solve"] * (1 + args.refine))
+    launches_step = int(st["launches_factor"] + st["launches_solve"] * nsw + 5 * nres)
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample ------------
     cpu = None
@@ -344,7 +349,8 @@ def run_b200(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": config_dict(args, desc, st, {
-                    "hessian_mode": method, "ordering": args.ordering, "refine_steps": args.refine,
+                    "hessian_mode": method, "ordering": args.ordering, "refine_steps_max": args.refine, "refine_tol": 1e-13,
+                    "solve_sweeps_used": nsw,
                     "nsuper": int(st["nsuper"]), "nlevels": int(st["nlevels"]),
                     "max_front": int(st["max_front"]), "parallelism": f"replicas x{world}"}),
                 "phase_ms": {"assemble": ph[0], "factor": ph[1], "solve": ph[2]},

@@ -158,6 +158,8 @@ int b2_timer_stop(b2_handle* h, double* ms) {
   return 0;
 }
 
+int b2_last_sweeps(const b2_handle* h) { return h ? h->eng.last_sweeps : -1; }
+
 int b2_get_perm(const b2_handle* h, int64_t* perm0) {
   if (!h || !perm0) return fail("b2_get_perm: NULL argument");
   for (int64_t k = 0; k < h->eng.sym.N; k++) perm0[k] = h->eng.sym.perm[k];
@@ -191,6 +193,7 @@ int b2_get_d(b2_handle* h, double* d) {
 int b2_set_option(b2_handle* h, const char* key, double value) {
   if (!h || !key) return fail("b2_set_option: NULL argument");
   if (!strcmp(key, "use_graph")) { h->eng.use_graph = value != 0; return 0; }
+  if (!strcmp(key, "refine_tol")) { h->eng.refine_tol = value; return 0; }
   return fail("b2_set_option: unknown key");
 }
 

@@ -138,6 +138,24 @@ int Engine::build_plan() {
       if (U.count) fact_launches.push_back(U);
     }
   }
+  // staging area of the factored diagonal blocks + the write-back launch that ends a factorization
+  {
+    std::vector<int64_t> dsptr(S.nsuper + 1, 0);
+    Launch W; W.kind = LK_DIAG_WRITEBACK; W.off = (int64_t)items.size();
+    int64_t off = 0;
+    for (int s = 0; s < S.nsuper; s++) {
+      dsptr[s] = off;
+      if (front_m(s) <= (int)small_max_m) continue;
+      int nblk = (front_w(s) + NB - 1) / NB;
+      for (int bi = 0; bi < nblk; bi++) { items.push_back(s); items.push_back(bi); W.count++; }
+      off += (int64_t)nblk * NB * NB;
+    }
+    dsptr[S.nsuper] = off;
+    if (W.count) fact_launches.push_back(W);
+    if (upload(&d_dsptr, dsptr, bytes_device)) return -1;
+    if (dalloc(&d_dstage, (size_t)off, bytes_device)) return -1;
+    plan.dstage = d_dstage; plan.dsptr = d_dsptr;
+  }
   std::reverse(bwd_launches.begin(), bwd_launches.end());
   if (upload(&d_items, items, bytes_device)) return -1;
   return 0;
@@ -202,6 +220,7 @@ int Engine::init(int dev) {
   const int big = 200 * 1024;
   B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
   B2_CUDA_OK(cudaFuncSetAttribute(k_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_bwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaDeviceSynchronize());
@@ -218,7 +237,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);
@@ -241,7 +260,10 @@ int Engine::run_factor_launches() {
         B2_LAUNCH(k_assemble_large, L.count, 256, 0, stream, plan, it, L.count);
         break;
       case LK_TRSM:
-        B2_LAUNCH(k_trsm, L.count, TRSM_ROWS, 0, stream, plan, it, L.count, L.jb);
+        B2_LAUNCH(k_trsm, L.count, TRSM_ROWS, TRSM_SMEM, stream, plan, it, L.count, L.jb);
+        break;
+      case LK_DIAG_WRITEBACK:
+        B2_LAUNCH(k_diag_writeback, L.count, 256, 0, stream, plan, it, L.count);
         break;
       case LK_UPDATE:
         B2_LAUNCH(k_update, L.count, 256, 0, stream, plan, it, L.count, L.jb, NB, L.mode);
@@ -407,19 +429,33 @@ int Engine::solve_core(const double* d_b, double* d_o, int negate, int refine_st
     return 0;
   };
   if (one_solve(d_b, 0)) return -1;
+  last_sweeps = 1;
+  const bool adaptive = refine_steps > 0 && refine_tol > 0;
   const bool need_res = refine_steps > 0 || relres != nullptr;
-  for (int it = 0; it <= refine_steps && need_res; it++) {
-    B2_LAUNCH(k_residual, nb, 256, 0, stream, N, d_Sp, d_Sj, d_Sslot, d_nzval, d_sol, d_b, d_res);
-    if (it == refine_steps) break;
-    if (one_solve(d_res, 1)) return -1;
-  }
-  if (relres) {
+  auto norms = [&]() -> int {   // h_scalars[0] = ||res||^2, [1] = ||b||^2 (valid after a stream sync)
     int pb = (int)std::min<int64_t>(nb, 512);
     B2_LAUNCH(k_sumsq, pb, 256, 0, stream, N, d_res, d_part);
     B2_LAUNCH(k_fold, 1, 256, 0, stream, pb, d_part, d_part + 1024);
     B2_LAUNCH(k_sumsq, pb, 256, 0, stream, N, d_b, d_part);
     B2_LAUNCH(k_fold, 1, 256, 0, stream, pb, d_part, d_part + 1025);
     B2_CUDA_OK(cudaMemcpyAsync(h_scalars, d_part + 1024, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    return 0;
+  };
+  for (int it = 0; it <= refine_steps && need_res; it++) {
+    B2_LAUNCH(k_residual, nb, 256, 0, stream, N, d_Sp, d_Sj, d_Sslot, d_nzval, d_sol, d_b, d_res);
+    const bool last = it == refine_steps;
+    if (adaptive && !last) {
+      // refine only while the residual is above the tolerance (one 16-byte D2H + sync per check)
+      if (norms()) return -1;
+      B2_CUDA_OK(cudaStreamSynchronize(stream));
+      const double rr = h_scalars[1] > 0 ? std::sqrt(h_scalars[0] / h_scalars[1]) : std::sqrt(h_scalars[0]);
+      if (rr <= refine_tol) break;
+    } else if (last) {
+      if (relres && norms()) return -1;
+      break;
+    }
+    if (one_solve(d_res, 1)) return -1;
+    last_sweeps++;
   }
   B2_LAUNCH(k_scale_copy, nb, 256, 0, stream, N, d_sol, d_o, negate ? -1.0 : 1.0);
   B2_CUDA_OK(cudaGetLastError());

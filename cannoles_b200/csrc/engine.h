@@ -12,7 +12,7 @@ namespace b2 {
 enum LaunchKind : int {
   LK_FRONT_SMALL = 0,
   LK_ASSEMBLE_LARGE,
-  LK_DIAG_FACTOR,
+  LK_DIAG_WRITEBACK,
   LK_TRSM,
   LK_UPDATE,
   LK_FWD,
@@ -44,7 +44,8 @@ struct Engine {
           *d_child_idx = nullptr, *d_amap_slot = nullptr, *d_amap_pos = nullptr, *d_perm = nullptr;
   int64_t *d_rptr = nullptr, *d_lptr = nullptr, *d_cbptr = nullptr, *d_uptr = nullptr,
           *d_amap_ptr = nullptr;
-  double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr;
+  double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr, *d_dstage = nullptr;
+  int64_t* d_dsptr = nullptr;
   int* d_flags = nullptr;
   unsigned long long* d_counts = nullptr;
   int32_t* d_items = nullptr;
@@ -69,6 +70,8 @@ struct Engine {
   cudaGraphExec_t g_fact = nullptr, g_fwdbwd = nullptr;
 #endif
   bool use_graph = true;
+  double refine_tol = 0.0;  // > 0: stop refining as soon as ||K x - b|| / ||b|| <= refine_tol
+  int last_sweeps = 0;      // forward/backward sweeps used by the last solve
   std::vector<void*> registered;
 
   int init(int dev);

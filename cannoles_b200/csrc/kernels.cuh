@@ -209,99 +209,44 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
   }
 }
 
-// Pivot-free LDL^T of an nb x nb (nb <= 32) block stored column-major in shared memory
-// (S[i + j * ld], lower triangle), by ONE warp: lane i keeps row i in registers, the unscaled
-// column k travels through a small shared buffer (broadcast reads).  On return the strict lower
-// part holds L and the diagonal D.  Returns 1 if an exactly zero pivot was met.
-__device__ __forceinline__ int warp_ldlt32_smem(double* S, int ld, int nb, double* colbuf, int lane) {
-  double a[32];
-  B2_UNROLL
-  for (int j = 0; j < 32; j++) a[j] = (lane < nb && j <= lane) ? S[lane + j * ld] : 0.0;
-  int bad = 0;
-  B2_UNROLL
-  for (int k = 0; k < 32; k++) {
-    if (k < nb) {
-      const double dk = __shfl_sync(0xffffffffu, a[k], k);
-      const double aik = a[k];
-      const double lik = aik / dk;
-      if (dk == 0.0) bad = 1;
-      double* cbuf = colbuf + (k & 1) * 32;
-      cbuf[lane] = aik;
-      __syncwarp();
-      B2_UNROLL
-      for (int j = k + 1; j < 32; j++)
-        if (j < nb && lane >= j) a[j] -= lik * cbuf[j];
-      if (lane > k) a[k] = lik;
-    }
-  }
-  __syncwarp();
-  B2_UNROLL
-  for (int j = 0; j < 32; j++)
-    if (lane < nb && j <= lane) S[lane + j * ld] = a[j];
-  return bad;
-}
-
-// CTA-level LDL^T of an nb x nb block, nb <= 64, in shared memory S (ld = DIAG_LD):
-// [A11; A21 A22] -> warp LDL^T of A11, triangular solve for A21, Schur update of A22, warp LDL^T of
-// A22.  scratch: DIAG_SCRATCH doubles of shared memory.  Every thread of the CTA (NT threads,
-// NT >= 32) must call it.
+// CTA-level pivot-free LDL^T of an nb x nb block (nb <= NB) held column-major in shared memory
+// (S[i + j * DIAG_LD], lower triangle): right-looking column loop, all NT threads.  Deliberately
+// ROLLED loops: this code runs once per pivot block on the critical path, and straight-line
+// unrolled code (tens of KB) is instruction-fetch bound when executed cold.  cu / cl: NB doubles
+// of shared memory each.  On return the strict lower part holds L and the diagonal D.
 template <int NT>
-__device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* scratch, int* flags) {
+__device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* cu, double* cl, int* flags) {
   constexpr int ld = DIAG_LD;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n1 = min(nb, 32), n2 = nb - n1;
-  if (warp == 0) {
-    const int bad = warp_ldlt32_smem(S, ld, n1, scratch, lane);
-    if (bad && lane == 0) flags[0] = 1;
-  }
-  __syncthreads();
-  if (n2 > 0) {
-    // W = A21 L11^{-T} (kept in registers), L21 = W D1^{-1}; one row per lane of warp 0
-    if (warp == 0) {
-      double a[32];
-      B2_UNROLL
-      for (int k = 0; k < 32; k++) a[k] = (lane < n2 && k < n1) ? S[(32 + lane) + k * ld] : 0.0;
-      B2_UNROLL
-      for (int k = 1; k < 32; k++) {
-        double acc = a[k];
-        B2_UNROLL
-        for (int t = 0; t < k; t++) acc -= a[t] * S[k + t * ld];   // L11(k,t): broadcast read
-        a[k] = acc;
-      }
-      // scratch2[row][k] = W (for the Schur update), S <- L21
-      B2_UNROLL
-      for (int k = 0; k < 32; k++)
-        if (lane < n2 && k < n1) {
-          scratch[64 + lane * 33 + k] = a[k];
-          S[(32 + lane) + k * ld] = a[k] / S[k + k * ld];
-        }
+  const int tid = threadIdx.x;
+  const int ti = tid & 63, tj = tid >> 6;
+  for (int k = 0; k < nb; k++) {
+    const double dk = S[k + k * ld];
+    const int i = k + 1 + tid;
+    if (i < nb) {
+      const double a = S[i + k * ld];
+      const double l = a / dk;
+      cu[i] = a;
+      cl[i] = l;
+      S[i + k * ld] = l;
     }
+    if (tid == 0 && dk == 0.0) flags[0] = 1;
     __syncthreads();
-    // A22(i,j) -= sum_k W(i,k) L21(j,k), i >= j
-    for (int e = tid; e < 32 * 32; e += NT) {
-      const int i = e & 31, j = e >> 5;
-      if (i < n2 && j <= i) {
-        double acc = 0.0;
-        for (int k = 0; k < n1; k++) acc += scratch[64 + i * 33 + k] * S[(32 + j) + k * ld];
-        S[(32 + i) + (32 + j) * ld] -= acc;
-      }
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int bad = warp_ldlt32_smem(S + 32 + 32 * ld, ld, n2, scratch, lane);
-      if (bad && lane == 0) flags[0] = 1;
+    for (int j = k + 1 + tj; j < nb; j += NT / 64) {
+      const int ii = j + ti;
+      if (ii < nb) S[ii + j * ld] -= cl[ii] * cu[j];
     }
     __syncthreads();
   }
 }
-
-constexpr int DIAG_SCRATCH = 64 + 32 * 33;
 
 // item = (front, row chunk).  Every CTA first factors the nb x nb diagonal block (jb, jb) of the
-// panel in shared memory (redundantly: 4 us of work instead of one more launch on the critical
-// path; chunk 0 writes the factored block and its pivots back), then forms
-// L21 = A21 L11^{-T} D^{-1} for its TRSM_ROWS rows below the block: one row per thread, in two
-// halves of 32 columns to bound registers.
+// panel in shared memory (redundantly: a few us of work instead of one more launch on the
+// critical path; chunk 0 stores the factored block in the staging area -- NOT in the panel, which
+// sibling CTAs may still be reading -- and the pivots in dvec), then forms
+// L21 = A21 L11^{-T} D^{-1} for its TRSM_ROWS rows below the block: one row per thread, the row
+// staged in shared memory, substitution in 8-column blocks (rolled loops, 8 x 8 unrolled bodies).
+// Dynamic shared memory: TRSM_SMEM bytes.
+constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + 3 * NB) * (int)sizeof(double);
 __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
@@ -310,57 +255,81 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(PlanDev P, const int32_t* __
   const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
   const int nb = min(NB, w - jb);
   double* Lp = P.Lx + P.lptr[s];
-  __shared__ double L11[NB * DIAG_LD];   // column-major: strict lower = L11, diagonal = D
-  __shared__ double scratch[DIAG_SCRATCH];
-  __shared__ double dd[NB];
+  B2_DYN_SMEM(raw);
+  double* R = reinterpret_cast<double*>(raw);   // [NB][TRSM_ROWS]; its head doubles as the diagonal block S
+  double* S = R;                                // [NB x DIAG_LD] column-major (NB*DIAG_LD <= NB*TRSM_ROWS)
+  double* Lr = R + NB * TRSM_ROWS;              // [NB][NB] row-major copy of L11 (strict lower)
+  double* cu = Lr + NB * NB;
+  double* cl = cu + NB;
+  double* dd = cl + NB;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
     const int i = idx % NB, j = idx / NB;
-    L11[i + j * DIAG_LD] = (i < nb && j <= i) ? Lp[(jb + i) + (size_t)(jb + j) * m] : 0.0;
+    S[i + j * DIAG_LD] = (i < nb && j <= i) ? Lp[(jb + i) + (size_t)(jb + j) * m] : 0.0;
   }
   __syncthreads();
-  cta_ldlt64<TRSM_ROWS>(L11, nb, scratch, P.flags);
-  __syncthreads();
-  if (tid < NB) dd[tid] = (tid < nb) ? L11[tid + tid * DIAG_LD] : 1.0;
+  cta_ldlt64<TRSM_ROWS>(S, nb, cu, cl, P.flags);
   if (chunk == 0) {
+    double* stage = P.dstage + P.dsptr[s] + (size_t)(jb / NB) * NB * NB;
     for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
       const int i = idx % NB, j = idx / NB;
-      if (i < nb && j <= i) Lp[(jb + i) + (size_t)(jb + j) * m] = L11[i + j * DIAG_LD];
+      if (i < nb && j <= i) stage[i + j * NB] = S[i + j * DIAG_LD];
     }
-    if (tid < nb) P.dvec[c0 + jb + tid] = L11[tid + tid * DIAG_LD];
+    if (tid < nb) P.dvec[c0 + jb + tid] = S[tid + tid * DIAG_LD];
   }
-  __syncthreads();
+  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+    const int k = idx / NB, t = idx % NB;
+    Lr[k * NB + t] = (t < k && k < nb) ? S[k + t * DIAG_LD] : 0.0;
+  }
+  if (tid < NB) dd[tid] = (tid < nb) ? S[tid + tid * DIAG_LD] : 1.0;
+  __syncthreads();                               // S is dead from here on: R takes its place
   const int i = jb + nb + chunk * TRSM_ROWS + tid;
-  if (i >= m) return;
-  double a[32], a2[32];
-  B2_UNROLL
-  for (int k = 0; k < 32; k++) a[k] = (k < nb) ? Lp[i + (size_t)(jb + k) * m] : 0.0;
-  B2_UNROLL
-  for (int k = 1; k < 32; k++) {
-    double acc = a[k];
+  if (i >= m) return;                            // no barrier below
+  for (int k = 0; k < NB; k++) R[k * TRSM_ROWS + tid] = (k < nb) ? Lp[i + (size_t)(jb + k) * m] : 0.0;
+  for (int kb = 0; kb < nb; kb += 8) {
+    double a8[8];
     B2_UNROLL
-    for (int t = 0; t < k; t++) acc -= a[t] * L11[k + t * DIAG_LD];
-    a[k] = acc;
-  }
-  if (nb > 32) {
-    B2_UNROLL
-    for (int k = 0; k < 32; k++) a2[k] = (32 + k < nb) ? Lp[i + (size_t)(jb + 32 + k) * m] : 0.0;
-    B2_UNROLL
-    for (int k = 0; k < 32; k++) {
-      double acc = a2[k];
+    for (int kk = 0; kk < 8; kk++) a8[kk] = R[(kb + kk) * TRSM_ROWS + tid];
+    for (int tb = 0; tb < kb; tb += 8) {
+      double w8[8];
       B2_UNROLL
-      for (int t = 0; t < 32; t++) acc -= a[t] * L11[(32 + k) + t * DIAG_LD];
+      for (int t = 0; t < 8; t++) w8[t] = R[(tb + t) * TRSM_ROWS + tid];
       B2_UNROLL
-      for (int t = 0; t < k; t++) acc -= a2[t] * L11[(32 + k) + (32 + t) * DIAG_LD];
-      a2[k] = acc;
+      for (int kk = 0; kk < 8; kk++) {
+        const double* lrow = Lr + (kb + kk) * NB + tb;
+        B2_UNROLL
+        for (int t = 0; t < 8; t++) a8[kk] -= w8[t] * lrow[t];
+      }
     }
     B2_UNROLL
-    for (int k = 0; k < 32; k++)
-      if (32 + k < nb) Lp[i + (size_t)(jb + 32 + k) * m] = a2[k] / dd[32 + k];
+    for (int kk = 1; kk < 8; kk++) {
+      const double* lrow = Lr + (kb + kk) * NB + kb;
+      B2_UNROLL
+      for (int t = 0; t < kk; t++) a8[kk] -= a8[t] * lrow[t];
+    }
+    B2_UNROLL
+    for (int kk = 0; kk < 8; kk++) {
+      R[(kb + kk) * TRSM_ROWS + tid] = a8[kk];
+      if (kb + kk < nb) Lp[i + (size_t)(jb + kb + kk) * m] = a8[kk] / dd[kb + kk];
+    }
   }
-  B2_UNROLL
-  for (int k = 0; k < 32; k++)
-    if (k < nb) Lp[i + (size_t)(jb + k) * m] = a[k] / dd[k];
+}
+
+// item = (front, pivot block): copy a factored diagonal block from the staging area into the
+// panel (one launch at the end of the factorization, when nobody reads the unfactored blocks).
+__global__ void __launch_bounds__(256) k_diag_writeback(PlanDev P, const int32_t* __restrict__ items, int nitems) {
+  const int b = blockIdx.x;
+  if (b >= nitems) return;
+  const int s = items[2 * b], bi = items[2 * b + 1];
+  const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+  const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
+  const int jb = bi * NB, nb = min(NB, w - jb);
+  double* Lp = P.Lx + P.lptr[s];
+  const double* stage = P.dstage + P.dsptr[s] + (size_t)bi * NB * NB;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
+    const int i = idx % NB, j = idx / NB;
+    if (i < nb && j <= i) Lp[(jb + i) + (size_t)(jb + j) * m] = stage[i + j * NB];
+  }
 }
 
 // item = (front, tile row, tile col), tile row >= tile col.  C -= A diag(d) A'^T on one

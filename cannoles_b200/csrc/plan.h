@@ -21,6 +21,8 @@ struct PlanDev {
   double* Lx;
   double* CB;
   double* dvec;
+  double* dstage;         // factored diagonal blocks of the tiled fronts (NB x NB each)
+  const int64_t* dsptr;   // per front: offset into dstage (tiled fronts only)
   int* flags;  // [0] = breakdown (exact zero pivot seen)
 };
 

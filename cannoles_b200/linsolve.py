@@ -60,6 +60,9 @@ class B200Struct:
     when absent they are inferred at the first ``try_to_factorize`` and the symbolic analysis is
     done then.
 
+    ``refine_steps`` is the MAXIMUM number of iterative-refinement sweeps of ``solve_ldl``; a sweep
+    is taken only while ||K d + rhs|| / ||rhs|| > ``refine_tol`` (north_star bar: 1e-12).
+
     ``shift_retries=True`` uses the caller protocol of ``newton_system!``
     (reference/src/CaNNOLeS.jl:1023-1043): a call whose trailing rho segment is a non-zero
     constant is a retry of the previous call with only that segment changed, so nothing is
@@ -67,7 +70,8 @@ class B200Struct:
     """
 
     def __init__(self, N, rows, cols, vals, nvar=None, nequ=None, ncon=None, ordering=ORDER_ND,
-                 perm=None, device=0, refine_steps=1, shift_retries=True, pin=True, _lib=None):
+                 perm=None, device=0, refine_steps=1, refine_tol=1e-13, shift_retries=True, pin=True,
+                 _lib=None):
         self._lib = _lib if _lib is not None else _capi.load()
         self.N = int(N)
         self.rows = np.ascontiguousarray(rows, dtype=np.int64)
@@ -81,6 +85,7 @@ class B200Struct:
         self._perm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int64)
         self.device = int(device)
         self.refine_steps = int(refine_steps)
+        self.refine_tol = float(refine_tol)
         self.shift_retries = bool(shift_retries)
         self.pin = bool(pin)
         self._h = C.c_void_p()
@@ -107,6 +112,7 @@ class B200Struct:
                                          nvar, nequ, ncon, self.ordering, up, self.device,
                                          C.byref(self._h)))
         self._dims = (nvar, nequ, ncon)
+        self._check(self._lib.b2_set_option(self._h, b"refine_tol", self.refine_tol))
         if self.pin:
             self.register_host(self.vals)
 
@@ -179,6 +185,11 @@ class B200Struct:
         ms = np.zeros(5)
         self._check(self._lib.b2_last_timings(self._h, _pd(ms)))
         return dict(zip(("upload", "assemble", "factor", "solve", "download"), ms.tolist()))
+
+    @property
+    def last_sweeps(self) -> int:
+        """Forward/backward sweeps of the last solve (1 = no refinement was needed)."""
+        return int(self._lib.b2_last_sweeps(self._h))
 
     @property
     def perm(self):

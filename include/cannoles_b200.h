@@ -91,6 +91,9 @@ int b2_refactorize_shift(b2_handle* h, double rho, double delta_or_nan, double e
  * receives ||K x - rhs||_2 / ||rhs||_2 of the returned (un-negated) solution. */
 int b2_solve(b2_handle* h, const double* rhs, double* d_out, int negate, int refine_steps,
              double* relres);
+/* forward/backward sweeps the last solve used (1 + refinement sweeps actually taken); with
+ * b2_set_option(h, "refine_tol", tol > 0) refinement stops as soon as the residual is <= tol */
+int b2_last_sweeps(const b2_handle* h);
 
 /* Device-resident variants (inputs/outputs already in HBM); used to time the kernels alone. */
 int b2_factorize_dev(b2_handle* h, const double* d_vals, double eig_tol, int64_t* npos,

@@ -40,6 +40,27 @@ def test_tiled_path_multi_block_front(ctor, oracle_cls, monkeypatch):
     assert B.stats()["max_width"] > 128
 
 
+def test_tiled_path_multi_chunk_trsm(ctor, oracle_cls, monkeypatch):
+    """Order-260 dense front: the rows below the first pivot block span two k_trsm CTAs, so the
+    factored diagonal block must come from the staging area, not from the panel being read."""
+    monkeypatch.setenv("B2_SMALL_MAX_M", "8")
+    N, r, c, v = random_kkt(100, 130, 30, 0.5, 73)
+    ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 100, 130, 30, ordering=1)
+
+
+def test_adaptive_refinement_stops_early(ctor):
+    N, r, c, v = random_kkt(30, 40, 8, 0.2, 74)
+    B = ctor(N, r, c, v, nvar=30, nequ=40, ncon=8, refine_steps=3)
+    assert B.try_to_factorize(v, 30, 40, 8, EPS)
+    d = np.zeros(N)
+    B.solve_ldl(np.ones(N), d)
+    assert B.last_relres <= 1e-13 and B.last_sweeps <= 2
+    C = ctor(N, r, c, v, nvar=30, nequ=40, ncon=8, refine_steps=2, refine_tol=0.0)   # fixed sweeps
+    assert C.try_to_factorize(v, 30, 40, 8, EPS)
+    C.solve_ldl(np.ones(N), d)
+    assert C.last_sweeps == 3
+
+
 def test_golden_vectors(ctor):
     for name in ("mgh01con_first_kkt", "random_kkt_0", "random_kkt_1"):
         ec.check_golden(ctor, name)
