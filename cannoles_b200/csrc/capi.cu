@@ -158,6 +158,11 @@ int b2_timer_stop(b2_handle* h, double* ms) {
   return 0;
 }
 
+int b2_profile(b2_handle* h, int which, int max, int* kinds, int* cls, int* counts, double* ms, int* n) {
+  if (!h || !kinds || !cls || !counts || !ms || !n) return fail("b2_profile: NULL argument");
+  return h->eng.profile(which, max, kinds, cls, counts, ms, n);
+}
+
 int b2_last_sweeps(const b2_handle* h) { return h ? h->eng.last_sweeps : -1; }
 
 int b2_get_perm(const b2_handle* h, int64_t* perm0) {

@@ -42,6 +42,8 @@ double wall() {
 int Engine::build_plan() {
   const Symbolic& S = sym;
   std::vector<int32_t> items;
+  std::vector<int64_t> asm_cptr(1, 0);   // (tiled front, column block) -> children touching it
+  std::vector<int32_t> asm_ent;
   fact_launches.clear(); fwd_launches.clear(); bwd_launches.clear();
   n_small = n_large = 0;
   auto front_m = [&](int s) { return (int)(S.rptr[s + 1] - S.rptr[s]); };
@@ -89,10 +91,30 @@ int Engine::build_plan() {
       for (int s : large) {
         int m = front_m(s);
         int ncb = (m + ASM_COLS - 1) / ASM_COLS, nrb = (m + ASM_ROWS - 1) / ASM_ROWS;
+        // children (ascending, the extend-add order) bucketed by the column blocks they touch
+        const int gbase = (int)asm_cptr.size() - 1;
+        std::vector<std::vector<int32_t>> bucket(ncb);
+        for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
+          int c = S.child_idx[q];
+          int wc = front_w(c);
+          const int32_t* relc = &S.rel[S.rptr[c] + wc];
+          int rc = front_m(c) - wc;
+          int j = 0;
+          while (j < rc) {
+            int blk = relc[j] / ASM_COLS, ja = j;
+            while (j < rc && relc[j] / ASM_COLS == blk) j++;
+            bucket[blk].push_back(c); bucket[blk].push_back(ja); bucket[blk].push_back(j);
+          }
+        }
+        for (int cb = 0; cb < ncb; cb++) {
+          asm_ent.insert(asm_ent.end(), bucket[cb].begin(), bucket[cb].end());
+          asm_cptr.push_back((int64_t)asm_ent.size() / 3);
+        }
         for (int cb = 0; cb < ncb; cb++)
           for (int rb = 0; rb < nrb; rb++) {
             if ((rb + 1) * ASM_ROWS <= cb * ASM_COLS) continue;   // tile entirely above the diagonal
-            items.push_back(s); items.push_back(cb); items.push_back(rb); L.count++;
+            items.push_back(s); items.push_back(cb); items.push_back(rb); items.push_back(gbase + cb);
+            L.count++;
           }
       }
       fact_launches.push_back(L);
@@ -156,6 +178,9 @@ int Engine::build_plan() {
     if (dalloc(&d_dstage, (size_t)off, bytes_device)) return -1;
     plan.dstage = d_dstage; plan.dsptr = d_dsptr;
   }
+  if (upload(&d_asm_cptr, asm_cptr, bytes_device)) return -1;
+  if (upload(&d_asm_ent, asm_ent, bytes_device)) return -1;
+  plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent;
   std::reverse(bwd_launches.begin(), bwd_launches.end());
   if (upload(&d_items, items, bytes_device)) return -1;
   return 0;
@@ -237,7 +262,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);
@@ -246,54 +271,88 @@ void Engine::destroy() {
   if (stream) cudaStreamDestroy(stream);
 }
 
-int Engine::run_factor_launches() {
-  for (const Launch& L : fact_launches) {
-    const int32_t* it = d_items + L.off;
-    switch (L.kind) {
-      case LK_FRONT_SMALL:
-        if (L.cls == 0) B2_LAUNCH(k_front_small<32>, L.count, 32, L.smem, stream, plan, it, L.count);
-        else if (L.cls == 1) B2_LAUNCH(k_front_small<64>, L.count, 64, L.smem, stream, plan, it, L.count);
-        else if (L.cls == 2) B2_LAUNCH(k_front_small<128>, L.count, 128, L.smem, stream, plan, it, L.count);
-        else B2_LAUNCH(k_front_small<256>, L.count, 256, L.smem, stream, plan, it, L.count);
-        break;
-      case LK_ASSEMBLE_LARGE:
-        B2_LAUNCH(k_assemble_large, L.count, 256, 0, stream, plan, it, L.count);
-        break;
-      case LK_TRSM:
-        B2_LAUNCH(k_trsm, L.count, TRSM_ROWS, TRSM_SMEM, stream, plan, it, L.count, L.jb);
-        break;
-      case LK_DIAG_WRITEBACK:
-        B2_LAUNCH(k_diag_writeback, L.count, 256, 0, stream, plan, it, L.count);
-        break;
-      case LK_UPDATE:
-        B2_LAUNCH(k_update, L.count, 256, 0, stream, plan, it, L.count, L.jb, NB, L.mode);
-        break;
-      default: break;
-    }
+int Engine::launch_one(const Launch& L, int pass) {
+  const int32_t* it = d_items + L.off;
+  switch (L.kind) {
+    case LK_FRONT_SMALL:
+      if (L.cls == 0) B2_LAUNCH(k_front_small<32>, L.count, 32, L.smem, stream, plan, it, L.count);
+      else if (L.cls == 1) B2_LAUNCH(k_front_small<64>, L.count, 64, L.smem, stream, plan, it, L.count);
+      else if (L.cls == 2) B2_LAUNCH(k_front_small<128>, L.count, 128, L.smem, stream, plan, it, L.count);
+      else B2_LAUNCH(k_front_small<256>, L.count, 256, L.smem, stream, plan, it, L.count);
+      break;
+    case LK_ASSEMBLE_LARGE:
+      B2_LAUNCH(k_assemble_large, L.count, 256, 0, stream, plan, it, L.count);
+      break;
+    case LK_TRSM:
+      B2_LAUNCH(k_trsm, L.count, TRSM_ROWS, TRSM_SMEM, stream, plan, it, L.count, L.jb);
+      break;
+    case LK_DIAG_WRITEBACK:
+      B2_LAUNCH(k_diag_writeback, L.count, 256, 0, stream, plan, it, L.count);
+      break;
+    case LK_UPDATE:
+      B2_LAUNCH(k_update, L.count, 256, 0, stream, plan, it, L.count, L.jb, NB, L.mode);
+      break;
+    case LK_FWD:
+      if (L.cls == 0) B2_LAUNCH(k_fwd<32>, L.count, 32, L.smem, stream, plan, it, L.count, d_x, d_upd);
+      else if (L.cls == 1) B2_LAUNCH(k_fwd<64>, L.count, 64, L.smem, stream, plan, it, L.count, d_x, d_upd);
+      else if (L.cls == 2) B2_LAUNCH(k_fwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x, d_upd);
+      else B2_LAUNCH(k_fwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x, d_upd);
+      break;
+    case LK_BWD:
+      if (L.cls == 0) B2_LAUNCH(k_bwd<32>, L.count, 32, L.smem, stream, plan, it, L.count, d_x);
+      else if (L.cls == 1) B2_LAUNCH(k_bwd<64>, L.count, 64, L.smem, stream, plan, it, L.count, d_x);
+      else if (L.cls == 2) B2_LAUNCH(k_bwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x);
+      else B2_LAUNCH(k_bwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x);
+      break;
+    default: break;
   }
+  (void)pass;
+  return 0;
+}
+
+int Engine::run_factor_launches() {
+  for (const Launch& L : fact_launches) launch_one(L, 0);
   B2_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int Engine::run_solve_launches() {
-  for (int pass = 0; pass < 2; pass++) {
-    const std::vector<Launch>& LL = pass == 0 ? fwd_launches : bwd_launches;
-    for (const Launch& L : LL) {
-      const int32_t* it = d_items + L.off;
-      if (pass == 0) {
-        if (L.cls == 0) B2_LAUNCH(k_fwd<32>, L.count, 32, L.smem, stream, plan, it, L.count, d_x, d_upd);
-        else if (L.cls == 1) B2_LAUNCH(k_fwd<64>, L.count, 64, L.smem, stream, plan, it, L.count, d_x, d_upd);
-        else if (L.cls == 2) B2_LAUNCH(k_fwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x, d_upd);
-        else B2_LAUNCH(k_fwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x, d_upd);
-      } else {
-        if (L.cls == 0) B2_LAUNCH(k_bwd<32>, L.count, 32, L.smem, stream, plan, it, L.count, d_x);
-        else if (L.cls == 1) B2_LAUNCH(k_bwd<64>, L.count, 64, L.smem, stream, plan, it, L.count, d_x);
-        else if (L.cls == 2) B2_LAUNCH(k_bwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x);
-        else B2_LAUNCH(k_bwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x);
-      }
+  for (const Launch& L : fwd_launches) launch_one(L, 0);
+  for (const Launch& L : bwd_launches) launch_one(L, 1);
+  B2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Developer aid: replay the factorization (which = 0) or one forward+backward sweep (which = 1)
+// launch by launch, outside the CUDA graph, with an event after every launch: warm-cache
+// per-launch device times (ncu's are cold-cache).  Needs a previous factorize / solve.
+int Engine::profile(int which, int max, int* kinds, int* cls, int* counts, double* ms, int* n) {
+  if (!have_vals) { snprintf(g_last_error, sizeof(g_last_error), "b2_profile before any factorization"); return -2; }
+  B2_CUDA_OK(cudaSetDevice(device));
+  std::vector<const Launch*> LL;
+  if (which == 0) for (const Launch& L : fact_launches) LL.push_back(&L);
+  else { for (const Launch& L : fwd_launches) LL.push_back(&L); for (const Launch& L : bwd_launches) LL.push_back(&L); }
+  std::vector<cudaEvent_t> evs(LL.size() + 1);
+  for (auto& e : evs) B2_CUDA_OK(cudaEventCreate(&e));
+  for (int rep = 0; rep < 2; rep++) {   // second pass is the warm one
+    if (which == 0) B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
+    B2_CUDA_OK(cudaEventRecord(evs[0], stream));
+    for (size_t i = 0; i < LL.size(); i++) {
+      launch_one(*LL[i], 0);
+      B2_CUDA_OK(cudaEventRecord(evs[i + 1], stream));
     }
+    B2_CUDA_OK(cudaStreamSynchronize(stream));
   }
   B2_CUDA_OK(cudaGetLastError());
+  int cnt = 0;
+  for (size_t i = 0; i < LL.size() && cnt < max; i++, cnt++) {
+    float f = 0;
+    cudaEventElapsedTime(&f, evs[i], evs[i + 1]);
+    kinds[cnt] = LL[i]->kind; cls[cnt] = LL[i]->kind == LK_UPDATE ? LL[i]->mode : LL[i]->cls;
+    counts[cnt] = LL[i]->count; ms[cnt] = f;
+  }
+  *n = cnt;
+  for (auto& e : evs) cudaEventDestroy(e);
   return 0;
 }
 

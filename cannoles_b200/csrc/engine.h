@@ -45,7 +45,8 @@ struct Engine {
   int64_t *d_rptr = nullptr, *d_lptr = nullptr, *d_cbptr = nullptr, *d_uptr = nullptr,
           *d_amap_ptr = nullptr;
   double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr, *d_dstage = nullptr;
-  int64_t* d_dsptr = nullptr;
+  int64_t *d_dsptr = nullptr, *d_asm_cptr = nullptr;
+  int32_t* d_asm_ent = nullptr;
   int* d_flags = nullptr;
   unsigned long long* d_counts = nullptr;
   int32_t* d_items = nullptr;
@@ -79,6 +80,8 @@ struct Engine {
   int build_plan();
   int run_factor_launches();
   int run_solve_launches();
+  int launch_one(const Launch& L, int pass);
+  int profile(int which, int max, int* kinds, int* cls, int* counts, double* ms, int* n);
   int assemble_and_factor(double eig_tol, int64_t* npos, int64_t* nzero, int64_t* nneg, int* breakdown,
                           bool do_assemble);
   int factorize_host(const double* vals, double eig_tol, int64_t* npos, int64_t* nzero, int64_t* nneg,

@@ -134,15 +134,19 @@ __global__ void __launch_bounds__(NT) k_front_small(PlanDev P, const int32_t* __
 // pass with K = w forms the contribution block.
 // ------------------------------------------------------------------------------------------
 
-// item = (front, destination column block, destination row chunk).  The CTA owns the
-// ASM_ROWS x ASM_COLS destination tile in shared memory: zero, scatter the A entries of its
-// columns, add the children's contribution blocks one child after the other (fixed order =>
-// deterministic sums, no atomics), then write the tile once (panel columns j < w go to Lx, the
-// others to CB; only rows >= column are produced).
+// item = (front, destination column block, destination row chunk, global column-block id).
+// The CTA owns the ASM_ROWS x ASM_COLS destination tile in shared memory: zero, scatter the A
+// entries of its columns, add the children's contribution blocks one child after the other
+// (fixed order => deterministic sums, no atomics), then write the tile once (panel columns j < w
+// go to Lx, the others to CB; only rows >= column are produced).  Which children touch a column
+// block, and with which of their columns, is precomputed on the host (asm_cptr / asm_ent): a
+// front at the top of the tree has hundreds of small children and scanning them all per tile
+// was the whole cost of this kernel.
 __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t* __restrict__ items, int nitems) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
-  const int s = items[3 * b], j0 = items[3 * b + 1] * ASM_COLS, i0 = items[3 * b + 2] * ASM_ROWS;
+  const int s = items[4 * b], j0 = items[4 * b + 1] * ASM_COLS, i0 = items[4 * b + 2] * ASM_ROWS;
+  const int gcb = items[4 * b + 3];
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int64_t r0 = P.rptr[s];
   const int m = (int)(P.rptr[s + 1] - r0);
@@ -168,34 +172,32 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
     }
   }
   __syncthreads();
-  for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
-    const int c = P.child_idx[ci];
+  const bool one_chunk = m <= ASM_ROWS;
+  for (int64_t e = P.asm_cptr[gcb]; e < P.asm_cptr[gcb + 1]; e++) {
+    const int c = P.asm_ent[3 * e], ja = P.asm_ent[3 * e + 1], jz = P.asm_ent[3 * e + 2];
     const int wc = P.scol[c + 1] - P.scol[c];
     const int64_t rc0 = P.rptr[c] + wc;
     const int rc = (int)(P.rptr[c + 1] - rc0);
     const int32_t* relc = P.rel + rc0;
     const double* cb = P.CB + P.cbptr[c];
-    // child columns / rows whose destination falls in the tile: relc is increasing
-    int lo = 0, hi = rc;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < j0) lo = mid + 1; else hi = mid; }
-    const int ja = lo;
-    hi = rc;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < je) lo = mid + 1; else hi = mid; }
-    const int jz = lo;
-    if (ja < jz) {
-      lo = ja; hi = rc;   // rows >= column, so the row range starts no earlier than ja
+    int ia = ja, iz = rc;   // rows >= column, so the row range starts no earlier than ja
+    if (!one_chunk) {
+      int lo = ja, hi = rc;
       while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < i0) lo = mid + 1; else hi = mid; }
-      const int ia = lo;
+      ia = lo;
       hi = rc;
       while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < ie) lo = mid + 1; else hi = mid; }
-      const int iz = lo;
+      iz = lo;
+    }
+    if (ia < iz) {   // uniform over the CTA
       for (int j = ja + warp; j < jz; j += 8) {
         double* dst = &T[relc[j] - j0][0] - i0;
         const double* src = cb + (size_t)j * rc;
+#pragma unroll 4
         for (int i = max(ia, j) + lane; i < iz; i += 32) dst[relc[i]] += src[i];
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   double* Lp = P.Lx + P.lptr[s];
   double* cbp = P.CB + P.cbptr[s];
@@ -209,31 +211,69 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
   }
 }
 
-// CTA-level pivot-free LDL^T of an nb x nb block (nb <= NB) held column-major in shared memory
-// (S[i + j * DIAG_LD], lower triangle): right-looking column loop, all NT threads.  Deliberately
-// ROLLED loops: this code runs once per pivot block on the critical path, and straight-line
-// unrolled code (tens of KB) is instruction-fetch bound when executed cold.  cu / cl: NB doubles
-// of shared memory each.  On return the strict lower part holds L and the diagonal D.
+// CTA-level pivot-free LDL^T of an nb x nb block (nb <= NB = 64) held column-major in shared
+// memory (S[i + j * DIAG_LD], lower triangle), blocked in 8-column panels: warp 0 factors the
+// panel (row-per-lane in registers, two rows per lane, pivots and multipliers exchanged with
+// shuffles), then all NT threads apply the rank-8 update to the trailing columns.  16 barriers
+// instead of 128, small loop bodies (this runs cold, once per pivot block, on the critical path).
+// dsh: NB doubles of shared memory.  On return the strict lower part holds L, the diagonal D.
 template <int NT>
-__device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* cu, double* cl, int* flags) {
+__device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* dsh, int* flags) {
   constexpr int ld = DIAG_LD;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ti = tid & 63, tj = tid >> 6;
-  for (int k = 0; k < nb; k++) {
-    const double dk = S[k + k * ld];
-    const int i = k + 1 + tid;
-    if (i < nb) {
-      const double a = S[i + k * ld];
-      const double l = a / dk;
-      cu[i] = a;
-      cl[i] = l;
-      S[i + k * ld] = l;
+  for (int kb = 0; kb < nb; kb += 8) {
+    if (warp == 0) {
+      const int pw = min(8, nb - kb);
+      const int r0 = kb + lane, r1 = kb + 32 + lane;
+      double p0[8], p1[8];
+      B2_UNROLL
+      for (int c = 0; c < 8; c++) {
+        p0[c] = (r0 < nb && c < pw && kb + c <= r0) ? S[r0 + (kb + c) * ld] : 0.0;
+        p1[c] = (r1 < nb && c < pw) ? S[r1 + (kb + c) * ld] : 0.0;
+      }
+      int bad = 0;
+      B2_UNROLL
+      for (int c = 0; c < 8; c++) {
+        if (c < pw) {
+          const double dk = __shfl_sync(0xffffffffu, p0[c], c);   // row kb + c lives in lane c
+          if (dk == 0.0) bad = 1;
+          const double a0 = p0[c], a1 = p1[c];
+          const double l0 = a0 / dk, l1 = a1 / dk;
+          B2_UNROLL
+          for (int cc = c + 1; cc < 8; cc++) {
+            const double ajc = __shfl_sync(0xffffffffu, a0, cc);  // unscaled A(kb + cc, kb + c)
+            p0[cc] -= l0 * ajc;
+            p1[cc] -= l1 * ajc;
+          }
+          if (lane > c) p0[c] = l0;
+          p1[c] = l1;
+        }
+      }
+      B2_UNROLL
+      for (int c = 0; c < 8; c++) {
+        if (c < pw) {
+          if (r0 < nb && kb + c <= r0) S[r0 + (kb + c) * ld] = p0[c];
+          if (r1 < nb) S[r1 + (kb + c) * ld] = p1[c];
+          if (lane == c) dsh[kb + c] = p0[c];
+        }
+      }
+      if (bad && lane == 0) flags[0] = 1;
     }
-    if (tid == 0 && dk == 0.0) flags[0] = 1;
     __syncthreads();
-    for (int j = k + 1 + tj; j < nb; j += NT / 64) {
-      const int ii = j + ti;
-      if (ii < nb) S[ii + j * ld] -= cl[ii] * cu[j];
+    const int t0 = kb + 8;
+    if (t0 < nb) {
+#pragma unroll 2
+      for (int j = t0 + tj; j < nb; j += NT / 64) {
+        const int i = j + ti;
+        if (i < nb) {
+          double acc = 0.0;
+          B2_UNROLL
+          for (int c = 0; c < 8; c++)
+            acc += S[i + (kb + c) * ld] * (dsh[kb + c] * S[j + (kb + c) * ld]);
+          S[i + j * ld] -= acc;
+        }
+      }
     }
     __syncthreads();
   }
@@ -246,7 +286,7 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* cu, double
 // L21 = A21 L11^{-T} D^{-1} for its TRSM_ROWS rows below the block: one row per thread, the row
 // staged in shared memory, substitution in 8-column blocks (rolled loops, 8 x 8 unrolled bodies).
 // Dynamic shared memory: TRSM_SMEM bytes.
-constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + 3 * NB) * (int)sizeof(double);
+constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + 2 * NB) * (int)sizeof(double);
 __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
@@ -259,16 +299,15 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(PlanDev P, const int32_t* __
   double* R = reinterpret_cast<double*>(raw);   // [NB][TRSM_ROWS]; its head doubles as the diagonal block S
   double* S = R;                                // [NB x DIAG_LD] column-major (NB*DIAG_LD <= NB*TRSM_ROWS)
   double* Lr = R + NB * TRSM_ROWS;              // [NB][NB] row-major copy of L11 (strict lower)
-  double* cu = Lr + NB * NB;
-  double* cl = cu + NB;
-  double* dd = cl + NB;
+  double* dsh = Lr + NB * NB;
+  double* dd = dsh + NB;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
     const int i = idx % NB, j = idx / NB;
     S[i + j * DIAG_LD] = (i < nb && j <= i) ? Lp[(jb + i) + (size_t)(jb + j) * m] : 0.0;
   }
   __syncthreads();
-  cta_ldlt64<TRSM_ROWS>(S, nb, cu, cl, P.flags);
+  cta_ldlt64<TRSM_ROWS>(S, nb, dsh, P.flags);
   if (chunk == 0) {
     double* stage = P.dstage + P.dsptr[s] + (size_t)(jb / NB) * NB * NB;
     for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {

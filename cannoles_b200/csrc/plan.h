@@ -23,6 +23,8 @@ struct PlanDev {
   double* dvec;
   double* dstage;         // factored diagonal blocks of the tiled fronts (NB x NB each)
   const int64_t* dsptr;   // per front: offset into dstage (tiled fronts only)
+  const int64_t* asm_cptr; // per (tiled front, destination column block): range in asm_ent
+  const int32_t* asm_ent;  // triplets (child, first child column, end child column)
   int* flags;  // [0] = breakdown (exact zero pivot seen)
 };
 

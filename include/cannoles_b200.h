@@ -110,6 +110,10 @@ int b2_stats(const b2_handle* h, b2_stats_t* out);
 /* device milliseconds of the phases of the last call: [0] upload, [1] COO->CSC assembly,
  * [2] numeric factorization (+ inertia), [3] solve (+ refinement), [4] download */
 int b2_last_timings(const b2_handle* h, double* ms5);
+/* Developer aid: replay the factorization (which = 0) or one forward+backward sweep
+ * (which = 1) launch by launch outside the CUDA graph, an event after every launch; returns per
+ * launch the kernel kind, its class / mode, the CTA count and the warm-cache device time. */
+int b2_profile(b2_handle* h, int which, int max, int* kinds, int* cls, int* counts, double* ms, int* n);
 /* CUDA events on the handle's own stream (bench.py times K steps between the two; a
  * torch.cuda.Event would only see torch's current stream) */
 int b2_timer_start(b2_handle* h);
