@@ -44,12 +44,14 @@ int Engine::build_plan() {
   std::vector<int32_t> items;
   std::vector<int64_t> asm_cptr(1, 0);   // (tiled front, column block) -> children touching it
   std::vector<int32_t> asm_ent;
+  std::vector<int32_t> sb_ent, sb_flag(S.nsuper, 0);   // big-front solve: child entries, flag offsets
+  nsflag = 0;
   fact_launches.clear(); fwd_launches.clear(); bwd_launches.clear();
   n_small = n_large = 0;
   auto front_m = [&](int s) { return (int)(S.rptr[s + 1] - S.rptr[s]); };
   auto front_w = [&](int s) { return (int)(S.scol[s + 1] - S.scol[s]); };
   for (int l = 0; l < S.nlevels; l++) {
-    std::vector<int32_t> small[4], large, sol[4];
+    std::vector<int32_t> small[4], large, sol[4], big;
     int small_mmax[4] = {0, 0, 0, 0}, sol_mmax[4] = {0, 0, 0, 0};
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; q++) {
       int s = S.level_sn[q];
@@ -63,9 +65,13 @@ int Engine::build_plan() {
         large.push_back(s);
         n_large++;
       }
-      int c = solve_class(m);
-      sol[c].push_back(s);
-      sol_mmax[c] = std::max(sol_mmax[c], m);
+      if (m > (int)solve_big_m) {
+        big.push_back(s);
+      } else {
+        int c = solve_class(m);
+        sol[c].push_back(s);
+        sol_mmax[c] = std::max(sol_mmax[c], m);
+      }
     }
     for (int c = 0; c < 4; c++) {
       if (!small[c].empty()) {
@@ -84,6 +90,45 @@ int Engine::build_plan() {
         L.kind = LK_BWD;
         bwd_launches.push_back(L);
       }
+    }
+    if (!big.empty()) {   // multi-CTA solves: flag-chained chunks, items ordered so that waits look back
+      Launch F; F.kind = LK_FWD_BIG; F.off = (int64_t)items.size();
+      int rmax = 0;
+      for (int s : big) {
+        int w = front_w(s), m = front_m(s);
+        int nblk = (w + SB - 1) / SB, nbel = (m - w + SB - 1) / SB;
+        sb_flag[s] = (int32_t)nsflag;
+        nsflag += nblk;
+        rmax = std::max(rmax, m - w);
+        std::vector<std::vector<int32_t>> bucket(nblk + nbel);
+        for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
+          int c = S.child_idx[q];
+          int wc = front_w(c);
+          const int32_t* relc = &S.rel[S.rptr[c] + wc];
+          int rc = front_m(c) - wc;
+          auto chunk_of = [&](int row) { return row < w ? row / SB : nblk + (row - w) / SB; };
+          int k = 0;
+          while (k < rc) {
+            int ch = chunk_of(relc[k]), ka = k;
+            while (k < rc && chunk_of(relc[k]) == ch) k++;
+            bucket[ch].push_back(c); bucket[ch].push_back(ka); bucket[ch].push_back(k);
+          }
+        }
+        for (int c = 0; c < nblk + nbel; c++) {
+          int e0 = (int)(sb_ent.size() / 3);
+          sb_ent.insert(sb_ent.end(), bucket[c].begin(), bucket[c].end());
+          items.push_back(s); items.push_back(c); items.push_back(e0); items.push_back((int)(sb_ent.size() / 3));
+          F.count++;
+        }
+      }
+      fwd_launches.push_back(F);
+      Launch Bk; Bk.kind = LK_BWD_BIG; Bk.off = (int64_t)items.size();
+      Bk.smem = (int)((size_t)std::max(rmax, 1) * sizeof(double));
+      for (int s : big) {
+        int nblk = (front_w(s) + SB - 1) / SB;
+        for (int c = nblk - 1; c >= 0; c--) { items.push_back(s); items.push_back(c); Bk.count++; }
+      }
+      bwd_launches.push_back(Bk);
     }
     if (large.empty()) continue;
     {
@@ -181,6 +226,11 @@ int Engine::build_plan() {
   if (upload(&d_asm_cptr, asm_cptr, bytes_device)) return -1;
   if (upload(&d_asm_ent, asm_ent, bytes_device)) return -1;
   plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent;
+  if (upload(&d_sb_ent, sb_ent, bytes_device)) return -1;
+  if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
+  if (dalloc(&d_sflags, (size_t)(2 * nsflag), bytes_device)) return -1;
+  if (dalloc(&d_ypub, (size_t)S.N, bytes_device)) return -1;
+  plan.sb_ent = d_sb_ent; plan.sb_flag = d_sb_flag;
   std::reverse(bwd_launches.begin(), bwd_launches.end());
   if (upload(&d_items, items, bytes_device)) return -1;
   return 0;
@@ -246,6 +296,7 @@ int Engine::init(int dev) {
   B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_bwd_big, cudaFuncAttributeMaxDynamicSharedMemorySize, big - 48 * 1024));
   B2_CUDA_OK(cudaFuncSetAttribute(k_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_bwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaDeviceSynchronize());
@@ -262,7 +313,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_sb_ent, d_sb_flag, d_sflags, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);
@@ -284,7 +335,7 @@ int Engine::launch_one(const Launch& L, int pass) {
       B2_LAUNCH(k_assemble_large, L.count, 256, 0, stream, plan, it, L.count);
       break;
     case LK_TRSM:
-      B2_LAUNCH(k_trsm, L.count, TRSM_ROWS, TRSM_SMEM, stream, plan, it, L.count, L.jb);
+      B2_LAUNCH(k_trsm, L.count, TRSM_THREADS, TRSM_SMEM, stream, plan, it, L.count, L.jb);
       break;
     case LK_DIAG_WRITEBACK:
       B2_LAUNCH(k_diag_writeback, L.count, 256, 0, stream, plan, it, L.count);
@@ -304,6 +355,12 @@ int Engine::launch_one(const Launch& L, int pass) {
       else if (L.cls == 2) B2_LAUNCH(k_bwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x);
       else B2_LAUNCH(k_bwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x);
       break;
+    case LK_FWD_BIG:
+      B2_LAUNCH(k_fwd_big, L.count, 256, 0, stream, plan, it, L.count, d_x, d_upd, d_ypub, d_sflags);
+      break;
+    case LK_BWD_BIG:
+      B2_LAUNCH(k_bwd_big, L.count, 256, L.smem, stream, plan, it, L.count, d_x, d_sflags + nsflag);
+      break;
     default: break;
   }
   (void)pass;
@@ -317,11 +374,18 @@ int Engine::run_factor_launches() {
 }
 
 int Engine::run_solve_launches() {
+  if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_sflags, 0, (size_t)(2 * nsflag) * sizeof(int), stream));
   for (const Launch& L : fwd_launches) launch_one(L, 0);
   for (const Launch& L : bwd_launches) launch_one(L, 1);
   B2_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+#ifdef B2_TIMING
+extern "C" int b2_debug_clocks(long long* out64) {
+  return cudaMemcpyFromSymbol(out64, b2_dbg, 64 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // Developer aid: replay the factorization (which = 0) or one forward+backward sweep (which = 1)
 // launch by launch, outside the CUDA graph, with an event after every launch: warm-cache
@@ -336,6 +400,7 @@ int Engine::profile(int which, int max, int* kinds, int* cls, int* counts, doubl
   for (auto& e : evs) B2_CUDA_OK(cudaEventCreate(&e));
   for (int rep = 0; rep < 2; rep++) {   // second pass is the warm one
     if (which == 0) B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
+    else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_sflags, 0, (size_t)(2 * nsflag) * sizeof(int), stream));
     B2_CUDA_OK(cudaEventRecord(evs[0], stream));
     for (size_t i = 0; i < LL.size(); i++) {
       launch_one(*LL[i], 0);

@@ -17,6 +17,8 @@ enum LaunchKind : int {
   LK_UPDATE,
   LK_FWD,
   LK_BWD,
+  LK_FWD_BIG,
+  LK_BWD_BIG,
 };
 
 struct Launch {
@@ -34,6 +36,7 @@ struct Engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   double small_max_m = 128;  // fronts up to this order take the shared-memory path
+  double solve_big_m = 384;  // fronts above this order take the multi-CTA solve kernels
 
   // device buffers
   int32_t *d_slot_ptr = nullptr, *d_coo_sorted = nullptr;
@@ -46,7 +49,10 @@ struct Engine {
           *d_amap_ptr = nullptr;
   double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr, *d_dstage = nullptr;
   int64_t *d_dsptr = nullptr, *d_asm_cptr = nullptr;
-  int32_t* d_asm_ent = nullptr;
+  int32_t *d_asm_ent = nullptr, *d_sb_ent = nullptr, *d_sb_flag = nullptr;
+  int* d_sflags = nullptr;     // block flags of the big-front solves: [0, nsflag) forward, [nsflag, 2 nsflag) backward
+  int64_t nsflag = 0;
+  double* d_ypub = nullptr;    // unscaled forward solutions published between the CTAs of a big front
   int* d_flags = nullptr;
   unsigned long long* d_counts = nullptr;
   int32_t* d_items = nullptr;

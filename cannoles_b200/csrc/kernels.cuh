@@ -20,6 +20,15 @@
 
 namespace b2 {
 
+#ifdef B2_TIMING
+__device__ long long b2_dbg[64];
+#define B2_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] = clock64(); } while (0)
+#define B2_ACC(i, t0) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] += clock64() - (t0); } while (0)
+#else
+#define B2_TICK(i)
+#define B2_ACC(i, t0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // (1) COO -> CSC.  One thread per CSC slot; the duplicates of a slot are summed in increasing
 // COO index starting from +0.0, i.e. bit-for-bit the sums `set_vals!` forms.
@@ -212,70 +221,96 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
 }
 
 // CTA-level pivot-free LDL^T of an nb x nb block (nb <= NB = 64) held column-major in shared
-// memory (S[i + j * DIAG_LD], lower triangle), blocked in 8-column panels: warp 0 factors the
-// panel (row-per-lane in registers, two rows per lane, pivots and multipliers exchanged with
-// shuffles), then all NT threads apply the rank-8 update to the trailing columns.  16 barriers
-// instead of 128, small loop bodies (this runs cold, once per pivot block, on the critical path).
-// dsh: NB doubles of shared memory.  On return the strict lower part holds L, the diagonal D.
+// memory (S[i + j * DIAG_LD], lower triangle), blocked in 8-column panels.  Panel step, warp 0:
+// EVERY lane factors the 8 x 8 diagonal sub-block redundantly in registers (no shuffles on the
+// pivot chain; one reciprocal per pivot instead of divisions), then substitutes its two rows of
+// the panel against it; it leaves L in S and W = L D in Wd.  Then all NT threads apply the
+// rank-8 update to the trailing columns (row-per-thread, L(i,:) in registers, W broadcast).
+// 16 barriers, small loop bodies: this runs cold, once per pivot block, on the critical path.
+// Wd: NB x 8 doubles of shared memory.  On return strict lower = L, diagonal = D.
 template <int NT>
-__device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* dsh, int* flags) {
+__device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* flags) {
   constexpr int ld = DIAG_LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ti = tid & 63, tj = tid >> 6;
   for (int kb = 0; kb < nb; kb += 8) {
+#ifdef B2_TIMING
+    long long tp0 = clock64();
+#endif
+    const int pw = min(8, nb - kb);
     if (warp == 0) {
-      const int pw = min(8, nb - kb);
-      const int r0 = kb + lane, r1 = kb + 32 + lane;
-      double p0[8], p1[8];
+      double g[8][8], rd[8];
       B2_UNROLL
-      for (int c = 0; c < 8; c++) {
-        p0[c] = (r0 < nb && c < pw && kb + c <= r0) ? S[r0 + (kb + c) * ld] : 0.0;
-        p1[c] = (r1 < nb && c < pw) ? S[r1 + (kb + c) * ld] : 0.0;
-      }
+      for (int c = 0; c < 8; c++)
+        B2_UNROLL
+        for (int t = 0; t <= c; t++) g[c][t] = (c < pw) ? S[(kb + c) + (kb + t) * ld] : (c == t ? 1.0 : 0.0);
       int bad = 0;
       B2_UNROLL
       for (int c = 0; c < 8; c++) {
-        if (c < pw) {
-          const double dk = __shfl_sync(0xffffffffu, p0[c], c);   // row kb + c lives in lane c
-          if (dk == 0.0) bad = 1;
-          const double a0 = p0[c], a1 = p1[c];
-          const double l0 = a0 / dk, l1 = a1 / dk;
+        if (g[c][c] == 0.0) bad = 1;
+        rd[c] = __drcp_rn(g[c][c]);
+        B2_UNROLL
+        for (int r = c + 1; r < 8; r++) {
+          const double lrc = g[r][c] * rd[c];
           B2_UNROLL
-          for (int cc = c + 1; cc < 8; cc++) {
-            const double ajc = __shfl_sync(0xffffffffu, a0, cc);  // unscaled A(kb + cc, kb + c)
-            p0[cc] -= l0 * ajc;
-            p1[cc] -= l1 * ajc;
-          }
-          if (lane > c) p0[c] = l0;
-          p1[c] = l1;
+          for (int t = c + 1; t <= r; t++) g[r][t] -= lrc * g[t][c];   // column c still unscaled
         }
+        B2_UNROLL
+        for (int r = c + 1; r < 8; r++) g[r][c] *= rd[c];
       }
+      // now g[c][t] (t < c) = L8, g[c][c] = d_c.  Rows kb + lane and kb + 32 + lane of the panel:
+      // w[c] = a[c] - sum_{t<c} w[t] L8[c][t],  l[c] = w[c] / d_c
+      double wv2[2][8];
       B2_UNROLL
-      for (int c = 0; c < 8; c++) {
-        if (c < pw) {
-          if (r0 < nb && kb + c <= r0) S[r0 + (kb + c) * ld] = p0[c];
-          if (r1 < nb) S[r1 + (kb + c) * ld] = p1[c];
-          if (lane == c) dsh[kb + c] = p0[c];
+      for (int h = 0; h < 2; h++) {
+        const int row = kb + 32 * h + lane;
+        B2_UNROLL
+        for (int c = 0; c < 8; c++)
+          wv2[h][c] = (row < nb && c < pw && kb + c <= row) ? S[row + (kb + c) * ld] : 0.0;
+      }
+      __syncwarp();   // every lane has read the unfactored block before anyone overwrites it
+      B2_UNROLL
+      for (int h = 0; h < 2; h++) {
+        const int row = kb + 32 * h + lane;
+        double* wv = wv2[h];
+        B2_UNROLL
+        for (int c = 1; c < 8; c++)
+          B2_UNROLL
+          for (int t = 0; t < c; t++) wv[c] -= wv[t] * g[c][t];
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) {
+          if (row < nb && c < pw) {
+            if (kb + c < row) { S[row + (kb + c) * ld] = wv[c] * rd[c]; Wd[row * 8 + c] = wv[c]; }
+            else if (kb + c == row) S[row + row * ld] = g[c][c];
+          }
         }
       }
       if (bad && lane == 0) flags[0] = 1;
     }
     __syncthreads();
+    B2_ACC(10, tp0);
+#ifdef B2_TIMING
+    tp0 = clock64();
+#endif
     const int t0 = kb + 8;
     if (t0 < nb) {
+      // thread <-> (row i = t0 + (tid & 63), column parity): S(i,j) -= sum_c L(i,c) W(j,c), j <= i
+      const int i = t0 + (tid & 63);
+      if (i < nb) {
+        double li[8];
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) li[c] = (c < pw) ? S[i + (kb + c) * ld] : 0.0;
 #pragma unroll 2
-      for (int j = t0 + tj; j < nb; j += NT / 64) {
-        const int i = j + ti;
-        if (i < nb) {
+        for (int j = t0 + (tid >> 6); j <= i; j += NT / 64) {
+          const double* wj = Wd + j * 8;
           double acc = 0.0;
           B2_UNROLL
-          for (int c = 0; c < 8; c++)
-            acc += S[i + (kb + c) * ld] * (dsh[kb + c] * S[j + (kb + c) * ld]);
+          for (int c = 0; c < 8; c++) acc += li[c] * wj[c];
           S[i + j * ld] -= acc;
         }
       }
     }
     __syncthreads();
+    B2_ACC(11, tp0);
   }
 }
 
@@ -283,11 +318,12 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* dsh, int* 
 // panel in shared memory (redundantly: a few us of work instead of one more launch on the
 // critical path; chunk 0 stores the factored block in the staging area -- NOT in the panel, which
 // sibling CTAs may still be reading -- and the pivots in dvec), then forms
-// L21 = A21 L11^{-T} D^{-1} for its TRSM_ROWS rows below the block: one row per thread, the row
-// staged in shared memory, substitution in 8-column blocks (rolled loops, 8 x 8 unrolled bodies).
+// L21 = A21 L11^{-T} D^{-1} for its TRSM_ROWS rows below the block: two rows per thread (16
+// independent FMA chains hide the FP64 latency), rows staged in shared memory, substitution in
+// 8-column blocks (rolled loops, 8 x 8 unrolled bodies).
 // Dynamic shared memory: TRSM_SMEM bytes.
-constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + 2 * NB) * (int)sizeof(double);
-__global__ void __launch_bounds__(TRSM_ROWS) k_trsm(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb) {
+constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + NB * 8 + NB) * (int)sizeof(double);
+__global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
   const int s = items[2 * b], chunk = items[2 * b + 1];
@@ -299,59 +335,93 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(PlanDev P, const int32_t* __
   double* R = reinterpret_cast<double*>(raw);   // [NB][TRSM_ROWS]; its head doubles as the diagonal block S
   double* S = R;                                // [NB x DIAG_LD] column-major (NB*DIAG_LD <= NB*TRSM_ROWS)
   double* Lr = R + NB * TRSM_ROWS;              // [NB][NB] row-major copy of L11 (strict lower)
-  double* dsh = Lr + NB * NB;
-  double* dd = dsh + NB;
+  double* Wd = Lr + NB * NB;                    // [NB][8] scratch of cta_ldlt64
+  double* dd = Wd + NB * 8;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+#ifdef B2_TIMING
+  if (tid == 0 && blockIdx.x == 0) { b2_dbg[10] = 0; b2_dbg[11] = 0; }
+#endif
+  B2_TICK(0);
+  for (int idx = tid; idx < NB * NB; idx += TRSM_THREADS) {
     const int i = idx % NB, j = idx / NB;
     S[i + j * DIAG_LD] = (i < nb && j <= i) ? Lp[(jb + i) + (size_t)(jb + j) * m] : 0.0;
   }
   __syncthreads();
-  cta_ldlt64<TRSM_ROWS>(S, nb, dsh, P.flags);
+  B2_TICK(1);
+  cta_ldlt64<TRSM_THREADS>(S, nb, Wd, P.flags);
+  B2_TICK(2);
   if (chunk == 0) {
     double* stage = P.dstage + P.dsptr[s] + (size_t)(jb / NB) * NB * NB;
-    for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+    for (int idx = tid; idx < NB * NB; idx += TRSM_THREADS) {
       const int i = idx % NB, j = idx / NB;
       if (i < nb && j <= i) stage[i + j * NB] = S[i + j * DIAG_LD];
     }
     if (tid < nb) P.dvec[c0 + jb + tid] = S[tid + tid * DIAG_LD];
   }
-  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+  for (int idx = tid; idx < NB * NB; idx += TRSM_THREADS) {
     const int k = idx / NB, t = idx % NB;
     Lr[k * NB + t] = (t < k && k < nb) ? S[k + t * DIAG_LD] : 0.0;
   }
-  if (tid < NB) dd[tid] = (tid < nb) ? S[tid + tid * DIAG_LD] : 1.0;
+  if (tid < NB) dd[tid] = (tid < nb) ? __drcp_rn(S[tid + tid * DIAG_LD]) : 1.0;   // reciprocal pivots
   __syncthreads();                               // S is dead from here on: R takes its place
-  const int i = jb + nb + chunk * TRSM_ROWS + tid;
-  if (i >= m) return;                            // no barrier below
-  for (int k = 0; k < NB; k++) R[k * TRSM_ROWS + tid] = (k < nb) ? Lp[i + (size_t)(jb + k) * m] : 0.0;
+  B2_TICK(3);
+  // two rows per thread (tid and tid + TRSM_THREADS of the chunk): 16 independent FMA chains
+  const int ibase = jb + nb + chunk * TRSM_ROWS;
+  if (ibase + tid >= m) return;                  // no barrier below
+  const int iA = ibase + tid, iB = ibase + TRSM_THREADS + tid;
+  const bool vB = iB < m;
+  for (int k = 0; k < NB; k++) {
+    R[k * TRSM_ROWS + tid] = (k < nb) ? Lp[iA + (size_t)(jb + k) * m] : 0.0;
+    R[k * TRSM_ROWS + TRSM_THREADS + tid] = (k < nb && vB) ? Lp[iB + (size_t)(jb + k) * m] : 0.0;
+  }
+  B2_TICK(4);
   for (int kb = 0; kb < nb; kb += 8) {
-    double a8[8];
+    double a8[2][8];
     B2_UNROLL
-    for (int kk = 0; kk < 8; kk++) a8[kk] = R[(kb + kk) * TRSM_ROWS + tid];
+    for (int kk = 0; kk < 8; kk++) {
+      a8[0][kk] = R[(kb + kk) * TRSM_ROWS + tid];
+      a8[1][kk] = R[(kb + kk) * TRSM_ROWS + TRSM_THREADS + tid];
+    }
     for (int tb = 0; tb < kb; tb += 8) {
-      double w8[8];
+      double w8[2][8];
       B2_UNROLL
-      for (int t = 0; t < 8; t++) w8[t] = R[(tb + t) * TRSM_ROWS + tid];
+      for (int t = 0; t < 8; t++) {
+        w8[0][t] = R[(tb + t) * TRSM_ROWS + tid];
+        w8[1][t] = R[(tb + t) * TRSM_ROWS + TRSM_THREADS + tid];
+      }
       B2_UNROLL
       for (int kk = 0; kk < 8; kk++) {
         const double* lrow = Lr + (kb + kk) * NB + tb;
         B2_UNROLL
-        for (int t = 0; t < 8; t++) a8[kk] -= w8[t] * lrow[t];
+        for (int t = 0; t < 8; t++) {
+          const double l = lrow[t];
+          a8[0][kk] -= w8[0][t] * l;
+          a8[1][kk] -= w8[1][t] * l;
+        }
       }
     }
     B2_UNROLL
     for (int kk = 1; kk < 8; kk++) {
       const double* lrow = Lr + (kb + kk) * NB + kb;
       B2_UNROLL
-      for (int t = 0; t < kk; t++) a8[kk] -= a8[t] * lrow[t];
+      for (int t = 0; t < kk; t++) {
+        const double l = lrow[t];
+        a8[0][kk] -= a8[0][t] * l;
+        a8[1][kk] -= a8[1][t] * l;
+      }
     }
     B2_UNROLL
     for (int kk = 0; kk < 8; kk++) {
-      R[(kb + kk) * TRSM_ROWS + tid] = a8[kk];
-      if (kb + kk < nb) Lp[i + (size_t)(jb + kb + kk) * m] = a8[kk] / dd[kb + kk];
+      R[(kb + kk) * TRSM_ROWS + tid] = a8[0][kk];
+      R[(kb + kk) * TRSM_ROWS + TRSM_THREADS + tid] = a8[1][kk];
+      if (kb + kk < nb) {
+        const double rdk = dd[kb + kk];
+        Lp[iA + (size_t)(jb + kb + kk) * m] = a8[0][kk] * rdk;
+        if (vB) Lp[iB + (size_t)(jb + kb + kk) * m] = a8[1][kk] * rdk;
+      }
     }
   }
+  B2_TICK(5);
 }
 
 // item = (front, pivot block): copy a factored diagonal block from the staging area into the
@@ -426,9 +496,11 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
       Bs[buf][lk + 4 * p][lr] = rb[p];
     }
   };
+  B2_TICK(20);
   gload(0);
   sstore(0);
   __syncthreads();
+  B2_TICK(21);
   for (int c = 0; c < nchunk; c++) {
     const int buf = c & 1;
     if (c + 1 < nchunk) gload((c + 1) * KC);
@@ -447,6 +519,7 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
     if (c + 1 < nchunk) sstore(buf ^ 1);
     __syncthreads();
   }
+  B2_TICK(22);
   double* Cb = (mode == 0) ? Lp : (P.CB + P.cbptr[s]);
   B2_UNROLL
   for (int a = 0; a < 4; a++)
@@ -459,6 +532,7 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
         double* dst = (mode == 0) ? (Cb + ri + (size_t)cj * m) : (Cb + (ri - w) + (size_t)(cj - w) * r);
         *dst -= acc[a][cc][e];
       }
+  B2_TICK(23);
 }
 
 // pivot-sign counts (src/solver_types.jl:90-96): counts[0] = #{d > tol}, [1] = #{|d| <= tol},
@@ -597,6 +671,211 @@ __global__ void __launch_bounds__(NT) k_bwd(PlanDev P, const int32_t* __restrict
     __syncthreads();
   }
   for (int i = tid; i < w; i += NT) x[c0 + i] = xs[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// (3b) big fronts: the triangular solves of ONE front are spread over many CTAs, one per
+// 64-row chunk (forward) / 64-column block (backward), chained by flags in global memory: a CTA
+// only ever waits for CTAs with a smaller blockIdx of the same launch (the items are ordered
+// that way), so the waits cannot deadlock.  The strip of the panel a CTA needs next is
+// prefetched into registers BEFORE it waits, so the chain per block is: flag round trip +
+// 64 x 64 mat-vec + in-block substitution by one warp.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wait_flag(const int* flag) {
+#ifdef B2_EMULATE
+  // the emulator runs the CTAs one after the other in blockIdx order: the producer must be done
+  if (threadIdx.x == 0 && *flag == 0) { fprintf(stderr, "k_*_big: wait on a CTA that has not run\n"); abort(); }
+#else
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<const volatile int*>(flag) == 0) { }
+    __threadfence();
+  }
+#endif
+  __syncthreads();
+}
+
+__device__ __forceinline__ double ld_cg(const double* p) {
+#ifdef B2_EMULATE
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+
+// item = (front, chunk, first entry, end entry): chunk c < nblk owns pivot rows
+// [64c, min(64c+64, w)); chunk c >= nblk owns the rows [w + 64(c-nblk), ...) below the pivots.
+// entries (sb_ent triplets: child, first child row, end child row) list the child update vectors
+// that land in the chunk, in child order.
+__global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __restrict__ items, int nitems,
+                                                 double* __restrict__ x, double* __restrict__ upd,
+                                                 double* __restrict__ ypub, int* __restrict__ flags) {
+  const int b = blockIdx.x;
+  if (b >= nitems) return;
+  const int s = items[4 * b], c = items[4 * b + 1];
+  const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+  const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
+  const int nblk = (w + SB - 1) / SB;
+  const bool pivot = c < nblk;
+  const int i0 = pivot ? c * SB : w + (c - nblk) * SB;
+  const int nrow = min(SB, (pivot ? w : m) - i0);
+  const double* Lp = P.Lx + P.lptr[s];
+  int* fl = flags + P.sb_flag[s];
+  __shared__ double t[SB], yb[SB], red[4][SB];
+  __shared__ double Ld[SB * (SB + 1)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid & 63, q = tid >> 6;
+  if (tid < SB) t[tid] = (pivot && tid < nrow) ? x[c0 + i0 + tid] : 0.0;
+  __syncthreads();
+  for (int e = items[4 * b + 2]; e < items[4 * b + 3]; e++) {
+    const int ch = P.sb_ent[3 * e], ka = P.sb_ent[3 * e + 1], kz = P.sb_ent[3 * e + 2];
+    const int wc = P.scol[ch + 1] - P.scol[ch];
+    const int32_t* relc = P.rel + P.rptr[ch] + wc;
+    const double* uc = upd + P.uptr[ch];
+    for (int k = ka + tid; k < kz; k += 256) t[relc[k] - i0] += uc[k];
+    __syncthreads();
+  }
+  if (pivot) {  // own diagonal block, strict lower part (prefetched before any wait)
+    for (int e = tid; e < SB * SB; e += 256) {
+      const int i = e % SB, j = e / SB;
+      Ld[i + j * (SB + 1)] = (i < nrow && j < i) ? Lp[(i0 + i) + (size_t)(i0 + j) * m] : 0.0;
+    }
+  }
+  const int nprev = pivot ? c : nblk;
+  double lreg[16];
+  auto prefetch = [&](int blk) {
+    const int kw = min(SB, w - blk * SB);
+    B2_UNROLL
+    for (int k = 0; k < 16; k++) {
+      const int kk = q * 16 + k;
+      lreg[k] = (r < nrow && kk < kw) ? Lp[(i0 + r) + (size_t)(blk * SB + kk) * m] : 0.0;
+    }
+  };
+  if (nprev > 0) prefetch(0);
+  for (int blk = 0; blk < nprev; blk++) {
+    wait_flag(fl + blk);
+    if (tid < SB) yb[tid] = (blk * SB + tid < w) ? ld_cg(ypub + c0 + blk * SB + tid) : 0.0;
+    __syncthreads();
+    double acc = 0.0, acc2 = 0.0;
+    B2_UNROLL
+    for (int k = 0; k < 16; k += 2) {
+      acc += lreg[k] * yb[q * 16 + k];
+      acc2 += lreg[k + 1] * yb[q * 16 + k + 1];
+    }
+    red[q][r] = acc + acc2;
+    if (blk + 1 < nprev) prefetch(blk + 1);
+    __syncthreads();
+    if (tid < SB) t[tid] -= (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    __syncthreads();
+  }
+  if (pivot) {
+    // unit-lower substitution inside the block by warp 0: lane holds rows lane and lane + 32
+    if (warp == 0) {
+      double t0 = t[lane], t1 = t[lane + 32];
+      for (int k = 0; k < nrow; k++) {
+        const double yk = __shfl_sync(0xffffffffu, (k < 32) ? t0 : t1, k & 31);
+        const double* col = Ld + k * (SB + 1);
+        if (lane > k) t0 -= col[lane] * yk;
+        if (lane + 32 > k) t1 -= col[lane + 32] * yk;
+      }
+      t[lane] = t0;
+      t[lane + 32] = t1;
+    }
+    __syncthreads();
+    if (tid < nrow) {
+      ypub[c0 + i0 + tid] = t[tid];
+      x[c0 + i0 + tid] = t[tid] / P.dvec[c0 + i0 + tid];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) fl[c] = 1;
+  } else {
+    if (tid < nrow) upd[P.uptr[s] + (i0 - w) + tid] = t[tid];
+  }
+}
+
+// item = (front, column block), blocks of a front in DESCENDING order.
+__global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __restrict__ items, int nitems,
+                                                 double* __restrict__ x, int* __restrict__ flags) {
+  const int b = blockIdx.x;
+  if (b >= nitems) return;
+  const int s = items[2 * b], c = items[2 * b + 1];
+  const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+  const int64_t r0 = P.rptr[s];
+  const int m = (int)(P.rptr[s + 1] - r0);
+  const int nblk = (w + SB - 1) / SB;
+  const int j0 = c * SB, ncol = min(SB, w - j0);
+  const double* Lp = P.Lx + P.lptr[s];
+  int* fl = flags + P.sb_flag[s];
+  B2_DYN_SMEM(raw);
+  double* xb = reinterpret_cast<double*>(raw);        // x of the rows below the pivots (m - w)
+  __shared__ double sc[SB], xd[SB];
+  __shared__ double Ld[SB * (SB + 1)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < SB) sc[tid] = (tid < ncol) ? x[c0 + j0 + tid] : 0.0;
+  for (int i = w + tid; i < m; i += 256) xb[i - w] = x[P.rowidx[r0 + i]];
+  for (int e = tid; e < SB * SB; e += 256) {   // own diagonal block: Ld[i][j] = L(j0+i, j0+j), j < i
+    const int i = e % SB, j = e / SB;
+    Ld[i + j * (SB + 1)] = (i < ncol && j < i) ? Lp[(j0 + i) + (size_t)(j0 + j) * m] : 0.0;
+  }
+  __syncthreads();
+  // rows below the pivots: sc[k] -= sum_i L(i, j0+k) xb[i]; one warp per column, lanes over rows
+  for (int k = warp; k < ncol; k += 8) {
+    const double* col = Lp + (size_t)(j0 + k) * m;
+    double acc = 0.0, acc2 = 0.0;
+    int i = w + lane;
+    for (; i + 32 < m; i += 64) { acc += col[i] * xb[i - w]; acc2 += col[i + 32] * xb[i + 32 - w]; }
+    if (i < m) acc += col[i] * xb[i - w];
+    acc += acc2;
+    B2_UNROLL
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sc[k] -= acc;
+  }
+  // later pivot blocks of the same front, as they are published
+  double lreg[8][2];
+  auto prefetch = [&](int d) {
+    const int dw = min(SB, w - d * SB);
+    B2_UNROLL
+    for (int kk = 0; kk < 8; kk++) {
+      const int k = warp + 8 * kk;
+      const double* col = Lp + (size_t)(j0 + k) * m + d * SB;
+      lreg[kk][0] = (k < ncol && lane < dw) ? col[lane] : 0.0;
+      lreg[kk][1] = (k < ncol && lane + 32 < dw) ? col[lane + 32] : 0.0;
+    }
+  };
+  if (c + 1 < nblk) prefetch(nblk - 1);
+  for (int d = nblk - 1; d > c; d--) {
+    wait_flag(fl + d);
+    if (tid < SB) xd[tid] = (d * SB + tid < w) ? ld_cg(x + c0 + d * SB + tid) : 0.0;
+    __syncthreads();
+    double part[8];
+    B2_UNROLL
+    for (int kk = 0; kk < 8; kk++) part[kk] = lreg[kk][0] * xd[lane] + lreg[kk][1] * xd[lane + 32];
+    if (d - 1 > c) prefetch(d - 1);
+    B2_UNROLL
+    for (int kk = 0; kk < 8; kk++) {
+      double v = part[kk];
+      B2_UNROLL
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && warp + 8 * kk < ncol) sc[warp + 8 * kk] -= v;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // L_cc^T x = sc inside the block by warp 0: lane holds entries lane and lane + 32
+  if (warp == 0) {
+    double s0 = sc[lane], s1 = sc[lane + 32];
+    for (int k = ncol - 1; k >= 0; k--) {
+      const double xk = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);
+      // entries j < k: s_j -= L(j0+k, j0+j) xk = Ld[k + j*(SB+1)]
+      if (lane < k) s0 -= Ld[k + lane * (SB + 1)] * xk;
+      if (lane + 32 < k) s1 -= Ld[k + (lane + 32) * (SB + 1)] * xk;
+    }
+    if (lane < ncol) x[c0 + j0 + lane] = s0;
+    if (lane + 32 < ncol) x[c0 + j0 + lane + 32] = s1;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) fl[c] = 1;
 }
 
 __global__ void __launch_bounds__(256) k_perm_in(int64_t n, const int32_t* __restrict__ perm,

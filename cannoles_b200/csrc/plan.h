@@ -25,6 +25,8 @@ struct PlanDev {
   const int64_t* dsptr;   // per front: offset into dstage (tiled fronts only)
   const int64_t* asm_cptr; // per (tiled front, destination column block): range in asm_ent
   const int32_t* asm_ent;  // triplets (child, first child column, end child column)
+  const int32_t* sb_ent;   // big-front solve: triplets (child, first child row, end child row)
+  const int32_t* sb_flag;  // per front: offset of its block flags (big fronts only)
   int* flags;  // [0] = breakdown (exact zero pivot seen)
 };
 
@@ -32,9 +34,11 @@ constexpr int NB = 64;        // pivot block width of the tiled path (== TILE: t
 constexpr int TILE = 64;      // update tile (TILE x TILE per CTA)
 constexpr int UPD_KC = 16;    // K-chunk of k_update's shared-memory pipeline
 constexpr int DIAG_LD = 65;   // leading dimension of a diagonal block in shared memory
-constexpr int TRSM_ROWS = 128;
+constexpr int TRSM_THREADS = 128;
+constexpr int TRSM_ROWS = 256;  // rows of the panel per k_trsm CTA (two per thread)
 constexpr int ASM_COLS = 8;   // destination tile of k_assemble_large: ASM_ROWS x ASM_COLS
 constexpr int ASM_ROWS = 512;
-constexpr int SNB = 32;       // column block of the solve kernels
+constexpr int SNB = 32;       // column block of the one-CTA-per-front solve kernels
+constexpr int SB = 64;        // row chunk / column block of the multi-CTA solve of big fronts
 
 }  // namespace b2

@@ -228,6 +228,7 @@ template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; retu
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
 inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
+inline double __drcp_rn(double a) { return 1.0 / a; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }

@@ -61,6 +61,16 @@ def test_adaptive_refinement_stops_early(ctor):
     assert C.last_sweeps == 3
 
 
+@pytest.mark.parametrize("case", [(40, 50, 12, 0.1, 21, 0), (60, 70, 20, 0.5, 71, 1), (45, 60, 10, 0.8, 72, 0)])
+def test_multi_cta_solve_of_big_fronts(ctor, oracle_cls, monkeypatch, case):
+    """Every front of order > 4 through k_fwd_big / k_bwd_big (flag-chained 64-row chunks): fronts
+    with children, rows below the pivots, and a 150-wide pivot block spanning three chunks."""
+    monkeypatch.setenv("B2_SOLVE_BIG_M", "4")
+    nv, ne, nc, dens, seed, order = case
+    N, r, c, v = random_kkt(nv, ne, nc, dens, seed)
+    ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=order)
+
+
 def test_golden_vectors(ctor):
     for name in ("mgh01con_first_kkt", "random_kkt_0", "random_kkt_1"):
         ec.check_golden(ctor, name)
