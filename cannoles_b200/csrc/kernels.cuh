@@ -740,6 +740,7 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
       Ld[i + j * (SB + 1)] = (i < nrow && j < i) ? Lp[(i0 + i) + (size_t)(i0 + j) * m] : 0.0;
     }
   }
+  __syncthreads();   // Ld (and t) complete before warp 0 uses them: chunk 0 has no wait in between
   const int nprev = pivot ? c : nblk;
   double lreg[16];
   auto prefetch = [&](int blk) {
