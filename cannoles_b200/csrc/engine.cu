@@ -293,12 +293,12 @@ int Engine::init(int dev) {
   plan.nzval = d_nzval; plan.Lx = d_Lx; plan.CB = d_CB; plan.dvec = d_dvec; plan.flags = d_flags;
   if (build_plan()) return -1;
   const int big = 200 * 1024;
-  B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
   B2_CUDA_OK(cudaFuncSetAttribute(k_bwd_big, cudaFuncAttributeMaxDynamicSharedMemorySize, big - 48 * 1024));
-  B2_CUDA_OK(cudaFuncSetAttribute(k_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  B2_CUDA_OK(cudaFuncSetAttribute(k_bwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_fwd<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_bwd<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaDeviceSynchronize());
   t_plan = wall() - t0;
   return 0;
@@ -326,10 +326,10 @@ int Engine::launch_one(const Launch& L, int pass) {
   const int32_t* it = d_items + L.off;
   switch (L.kind) {
     case LK_FRONT_SMALL:
-      if (L.cls == 0) B2_LAUNCH(k_front_small<32>, L.count, 32, L.smem, stream, plan, it, L.count);
-      else if (L.cls == 1) B2_LAUNCH(k_front_small<64>, L.count, 64, L.smem, stream, plan, it, L.count);
-      else if (L.cls == 2) B2_LAUNCH(k_front_small<128>, L.count, 128, L.smem, stream, plan, it, L.count);
-      else B2_LAUNCH(k_front_small<256>, L.count, 256, L.smem, stream, plan, it, L.count);
+      if (L.cls == 0) { auto kfn = k_front_small<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, stream, plan, it, L.count, L.smem); }
+      else if (L.cls == 1) { auto kfn = k_front_small<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, stream, plan, it, L.count, 0); }
+      else if (L.cls == 2) { auto kfn = k_front_small<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, stream, plan, it, L.count, 0); }
+      else { auto kfn = k_front_small<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, stream, plan, it, L.count, 0); }
       break;
     case LK_ASSEMBLE_LARGE:
       B2_LAUNCH(k_assemble_large, L.count, 256, 0, stream, plan, it, L.count);
@@ -344,16 +344,16 @@ int Engine::launch_one(const Launch& L, int pass) {
       B2_LAUNCH(k_update, L.count, 256, 0, stream, plan, it, L.count, L.jb, NB, L.mode);
       break;
     case LK_FWD:
-      if (L.cls == 0) B2_LAUNCH(k_fwd<32>, L.count, 32, L.smem, stream, plan, it, L.count, d_x, d_upd);
-      else if (L.cls == 1) B2_LAUNCH(k_fwd<64>, L.count, 64, L.smem, stream, plan, it, L.count, d_x, d_upd);
-      else if (L.cls == 2) B2_LAUNCH(k_fwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x, d_upd);
-      else B2_LAUNCH(k_fwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x, d_upd);
+      if (L.cls == 0) { auto kfn = k_fwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, stream, plan, it, L.count, d_x, d_upd, L.smem); }
+      else if (L.cls == 1) { auto kfn = k_fwd<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, stream, plan, it, L.count, d_x, d_upd, 0); }
+      else if (L.cls == 2) { auto kfn = k_fwd<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, stream, plan, it, L.count, d_x, d_upd, 0); }
+      else { auto kfn = k_fwd<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, stream, plan, it, L.count, d_x, d_upd, 0); }
       break;
     case LK_BWD:
-      if (L.cls == 0) B2_LAUNCH(k_bwd<32>, L.count, 32, L.smem, stream, plan, it, L.count, d_x);
-      else if (L.cls == 1) B2_LAUNCH(k_bwd<64>, L.count, 64, L.smem, stream, plan, it, L.count, d_x);
-      else if (L.cls == 2) B2_LAUNCH(k_bwd<128>, L.count, 128, L.smem, stream, plan, it, L.count, d_x);
-      else B2_LAUNCH(k_bwd<256>, L.count, 256, L.smem, stream, plan, it, L.count, d_x);
+      if (L.cls == 0) { auto kfn = k_bwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, stream, plan, it, L.count, d_x, L.smem); }
+      else if (L.cls == 1) { auto kfn = k_bwd<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, stream, plan, it, L.count, d_x, 0); }
+      else if (L.cls == 2) { auto kfn = k_bwd<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, stream, plan, it, L.count, d_x, 0); }
+      else { auto kfn = k_bwd<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, stream, plan, it, L.count, d_x, 0); }
       break;
     case LK_FWD_BIG:
       B2_LAUNCH(k_fwd_big, L.count, 256, 0, stream, plan, it, L.count, d_x, d_upd, d_ypub, d_sflags);

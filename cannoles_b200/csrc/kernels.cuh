@@ -20,6 +20,9 @@
 
 namespace b2 {
 
+// barrier of the threads that share one front: the whole CTA, or one warp when FPB fronts share a CTA
+#define B2_FSYNC() do { if (FPB > 1) __syncwarp(); else __syncthreads(); } while (0)
+
 #ifdef B2_TIMING
 __device__ long long b2_dbg[64];
 #define B2_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] = clock64(); } while (0)
@@ -75,12 +78,16 @@ __global__ void __launch_bounds__(256) k_diag_shift(int n, const int32_t* __rest
 // zero -> scatter A -> extend-add children (fixed order, deterministic) -> eliminate w pivots
 // (right-looking, no pivoting) -> write panel, pivots and contribution block.
 // ------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(NT) k_front_small(PlanDev P, const int32_t* __restrict__ list, int count) {
-  const int b = blockIdx.x;
+template <int NT, int FPB>
+__global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32_t* __restrict__ list, int count,
+                                                          int fstride) {
+  // FPB > 1 (the 32-thread class): FPB fronts per CTA, one warp each, warp-level barriers only
+  const int slot = (FPB > 1) ? (int)(threadIdx.x >> 5) : 0;
+  const int b = blockIdx.x * FPB + slot;
   if (b >= count) return;
   const int s = list[b];
-  B2_DYN_SMEM(raw);
+  B2_DYN_SMEM(raw0);
+  unsigned char* raw = raw0 + (size_t)slot * fstride;
   double* F = reinterpret_cast<double*>(raw);
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int64_t r0 = P.rptr[s];
@@ -88,14 +95,14 @@ __global__ void __launch_bounds__(NT) k_front_small(PlanDev P, const int32_t* __
   const int r = m - w;
   double* lk = F + (size_t)m * m;
   double* ak = lk + m;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = (FPB > 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;
 
   for (int idx = tid; idx < m * m; idx += NT) F[idx] = 0.0;
-  __syncthreads();
+  B2_FSYNC();
   for (int64_t q = P.amap_ptr[s] + tid; q < P.amap_ptr[s + 1]; q += NT)
     F[P.amap_pos[q]] = P.nzval[P.amap_slot[q]];
-  __syncthreads();
+  B2_FSYNC();
   for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
     const int c = P.child_idx[ci];
     const int wc = P.scol[c + 1] - P.scol[c];
@@ -107,8 +114,9 @@ __global__ void __launch_bounds__(NT) k_front_small(PlanDev P, const int32_t* __
       const int J = relc[j];
       for (int i = j + lane; i < rc; i += 32) F[relc[i] + J * m] += cb[i + (size_t)j * rc];
     }
-    __syncthreads();
+    B2_FSYNC();
   }
+  // eliminate the w pivot columns: rank-1 updates restricted to the pivot columns ...
   for (int k = 0; k < w; k++) {
     const double dk = F[k + k * m];
     for (int i = k + 1 + tid; i < m; i += NT) {
@@ -122,12 +130,39 @@ __global__ void __launch_bounds__(NT) k_front_small(PlanDev P, const int32_t* __
       P.dvec[c0 + k] = dk;
       if (dk == 0.0) P.flags[0] = 1;
     }
-    __syncthreads();
-    for (int j = k + 1 + warp; j < m; j += NW) {
+    B2_FSYNC();
+    for (int j = k + 1 + warp; j < w; j += NW) {
       const double ajk = ak[j];
       for (int i = j + lane; i < m; i += 32) F[i + j * m] -= lk[i] * ajk;
     }
-    __syncthreads();
+    B2_FSYNC();
+  }
+  // ... then ONE rank-w update of the contribution block, C -= L21 D L21^T, in 8 x 8 x 4 FP64
+  // tensor-core tiles straight from shared memory (d_k sits on the diagonal of the panel)
+  if (r > 0) {
+    const int nt8 = (r + 7) >> 3;
+    const int g = lane >> 2, t = lane & 3;
+    for (int tile = warp; tile < nt8 * nt8; tile += NW) {
+      const int tj = tile / nt8, ti = tile - tj * nt8;
+      if (ti < tj) continue;
+      const int ra = w + ti * 8 + g, rb = w + tj * 8 + g;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int k0 = 0; k0 < w; k0 += 4) {
+        const int k = k0 + t;
+        double av = 0.0, bv = 0.0;
+        if (k < w) {
+          if (ra < m) av = F[ra + k * m];
+          if (rb < m) bv = F[rb + k * m] * F[k + k * m];
+        }
+        dmma_8x8x4(acc0, acc1, av, bv);
+      }
+      const int cj = w + tj * 8 + 2 * t;
+      if (ra < m) {
+        if (cj < m && ra >= cj) F[ra + cj * m] -= acc0;
+        if (cj + 1 < m && ra >= cj + 1) F[ra + (cj + 1) * m] -= acc1;
+      }
+    }
+    B2_FSYNC();
   }
   double* Lp = P.Lx + P.lptr[s];
   for (int idx = tid; idx < m * w; idx += NT) Lp[idx] = F[idx];
@@ -220,6 +255,24 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
   }
 }
 
+// 1 / d to (nearly) full double precision on a SHORT dependent chain: FP32 reciprocal as the seed
+// (24 bits), two Newton steps in FP64 (4 dependent DFMAs instead of the ~8 of __drcp_rn).  The
+// reciprocal of a pivot sits on the critical path of every elimination step.
+__device__ __forceinline__ double fast_rcp(double d) {
+#ifdef B2_EMULATE
+  return 1.0 / d;
+#else
+  const double ad = fabs(d);
+  if (!(ad > 1e-30 && ad < 1e30)) return __drcp_rn(d);
+  double x = (double)__frcp_rn((float)d);
+  double e = __fma_rn(-d, x, 1.0);
+  x = __fma_rn(x, e, x);
+  e = __fma_rn(-d, x, 1.0);
+  x = __fma_rn(x, e, x);
+  return x;
+#endif
+}
+
 // CTA-level pivot-free LDL^T of an nb x nb block (nb <= NB = 64) held column-major in shared
 // memory (S[i + j * DIAG_LD], lower triangle), blocked in 8-column panels.  Panel step, warp 0:
 // EVERY lane factors the 8 x 8 diagonal sub-block redundantly in registers (no shuffles on the
@@ -247,7 +300,7 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
       B2_UNROLL
       for (int c = 0; c < 8; c++) {
         if (g[c][c] == 0.0) bad = 1;
-        rd[c] = __drcp_rn(g[c][c]);
+        rd[c] = fast_rcp(g[c][c]);
         B2_UNROLL
         for (int r = c + 1; r < 8; r++) {
           const double lrc = g[r][c] * rd[c];
@@ -299,13 +352,13 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
         double li[8];
         B2_UNROLL
         for (int c = 0; c < 8; c++) li[c] = (c < pw) ? S[i + (kb + c) * ld] : 0.0;
-#pragma unroll 2
+#pragma unroll 4
         for (int j = t0 + (tid >> 6); j <= i; j += NT / 64) {
           const double* wj = Wd + j * 8;
-          double acc = 0.0;
+          double acc0 = 0.0, acc1 = 0.0;
           B2_UNROLL
-          for (int c = 0; c < 8; c++) acc += li[c] * wj[c];
-          S[i + j * ld] -= acc;
+          for (int c = 0; c < 8; c += 2) { acc0 += li[c] * wj[c]; acc1 += li[c + 1] * wj[c + 1]; }
+          S[i + j * ld] -= acc0 + acc1;
         }
       }
     }
@@ -382,6 +435,9 @@ __global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t*
       a8[0][kk] = R[(kb + kk) * TRSM_ROWS + tid];
       a8[1][kk] = R[(kb + kk) * TRSM_ROWS + TRSM_THREADS + tid];
     }
+    double b8[2][8];   // second set of partial sums: 32 independent FMA chains per thread
+    B2_UNROLL
+    for (int kk = 0; kk < 8; kk++) { b8[0][kk] = 0.0; b8[1][kk] = 0.0; }
     for (int tb = 0; tb < kb; tb += 8) {
       double w8[2][8];
       B2_UNROLL
@@ -393,13 +449,17 @@ __global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t*
       for (int kk = 0; kk < 8; kk++) {
         const double* lrow = Lr + (kb + kk) * NB + tb;
         B2_UNROLL
-        for (int t = 0; t < 8; t++) {
-          const double l = lrow[t];
-          a8[0][kk] -= w8[0][t] * l;
-          a8[1][kk] -= w8[1][t] * l;
+        for (int t = 0; t < 8; t += 2) {
+          const double l0 = lrow[t], l1 = lrow[t + 1];
+          a8[0][kk] -= w8[0][t] * l0;
+          a8[1][kk] -= w8[1][t] * l0;
+          b8[0][kk] -= w8[0][t + 1] * l1;
+          b8[1][kk] -= w8[1][t + 1] * l1;
         }
       }
     }
+    B2_UNROLL
+    for (int kk = 0; kk < 8; kk++) { a8[0][kk] += b8[0][kk]; a8[1][kk] += b8[1][kk]; }
     B2_UNROLL
     for (int kk = 1; kk < 8; kk++) {
       const double* lrow = Lr + (kb + kk) * NB + kb;
@@ -498,6 +558,20 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
   };
   B2_TICK(20);
   gload(0);
+  // the C tile is read now (its latency hides behind the K loop) and written once at the end
+  double* Cb = (mode == 0) ? Lp : (P.CB + P.cbptr[s]);
+  double cold[4][2][2];
+  B2_UNROLL
+  for (int a = 0; a < 4; a++)
+    B2_UNROLL
+    for (int cc = 0; cc < 2; cc++)
+      B2_UNROLL
+      for (int e = 0; e < 2; e++) {
+        const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
+        const bool ok = ri < m && cj < jend && ri >= cj;
+        const double* src = (mode == 0) ? (Cb + ri + (size_t)cj * m) : (Cb + (ri - w) + (size_t)(cj - w) * r);
+        cold[a][cc][e] = ok ? *src : 0.0;
+      }
   sstore(0);
   __syncthreads();
   B2_TICK(21);
@@ -520,7 +594,6 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
     __syncthreads();
   }
   B2_TICK(22);
-  double* Cb = (mode == 0) ? Lp : (P.CB + P.cbptr[s]);
   B2_UNROLL
   for (int a = 0; a < 4; a++)
     B2_UNROLL
@@ -530,7 +603,7 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
         const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
         if (ri >= m || cj >= jend || ri < cj) continue;
         double* dst = (mode == 0) ? (Cb + ri + (size_t)cj * m) : (Cb + (ri - w) + (size_t)(cj - w) * r);
-        *dst -= acc[a][cc][e];
+        *dst = cold[a][cc][e] - acc[a][cc][e];
       }
   B2_TICK(23);
 }
@@ -569,20 +642,23 @@ __global__ void __launch_bounds__(256) k_inertia(const double* __restrict__ d, i
 //           x(pivots) <- y / D
 // backward: x(pivots) <- L11^{-T} (z - L21^T x(rows below))
 // ------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(NT) k_fwd(PlanDev P, const int32_t* __restrict__ list, int count,
-                                            double* __restrict__ x, double* __restrict__ upd) {
-  const int b = blockIdx.x;
+template <int NT, int FPB>
+__global__ void __launch_bounds__(NT * FPB) k_fwd(PlanDev P, const int32_t* __restrict__ list, int count,
+                                                  double* __restrict__ x, double* __restrict__ upd, int fstride) {
+  // FPB > 1 (the 32-thread class): FPB fronts per CTA, one warp each, warp-level barriers only
+  const int slot = (FPB > 1) ? (int)(threadIdx.x >> 5) : 0;
+  const int b = blockIdx.x * FPB + slot;
   if (b >= count) return;
   const int s = list[b];
-  B2_DYN_SMEM(raw);
+  B2_DYN_SMEM(raw0);
+  unsigned char* raw = raw0 + (size_t)slot * fstride;
   double* xs = reinterpret_cast<double*>(raw);
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = (FPB > 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* Lp = P.Lx + P.lptr[s];
   for (int i = tid; i < m; i += NT) xs[i] = (i < w) ? x[c0 + i] : 0.0;
-  __syncthreads();
+  B2_FSYNC();
   for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
     const int c = P.child_idx[ci];
     const int wc = P.scol[c + 1] - P.scol[c];
@@ -591,7 +667,7 @@ __global__ void __launch_bounds__(NT) k_fwd(PlanDev P, const int32_t* __restrict
     const int32_t* relc = P.rel + rc0;
     const double* uc = upd + P.uptr[c];
     for (int k = tid; k < rc; k += NT) xs[relc[k]] += uc[k];
-    __syncthreads();
+    B2_FSYNC();
   }
   for (int jb = 0; jb < w; jb += SNB) {
     const int nb = min(SNB, w - jb);
@@ -608,7 +684,7 @@ __global__ void __launch_bounds__(NT) k_fwd(PlanDev P, const int32_t* __restrict
       }
       if (lane < nb) xs[jb + lane] = y;
     }
-    __syncthreads();
+    B2_FSYNC();
     for (int i = jb + nb + tid; i < m; i += NT) {
       double acc = 0.0;
       B2_UNROLL
@@ -616,30 +692,33 @@ __global__ void __launch_bounds__(NT) k_fwd(PlanDev P, const int32_t* __restrict
         if (k < nb) acc += Lp[i + (size_t)(jb + k) * m] * xs[jb + k];
       xs[i] -= acc;
     }
-    __syncthreads();
+    B2_FSYNC();
   }
   for (int i = tid; i < w; i += NT) x[c0 + i] = xs[i] / P.dvec[c0 + i];
   double* us = upd + P.uptr[s];
   for (int i = w + tid; i < m; i += NT) us[i - w] = xs[i];
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) k_bwd(PlanDev P, const int32_t* __restrict__ list, int count,
-                                            double* __restrict__ x) {
-  const int b = blockIdx.x;
+template <int NT, int FPB>
+__global__ void __launch_bounds__(NT * FPB) k_bwd(PlanDev P, const int32_t* __restrict__ list, int count,
+                                                  double* __restrict__ x, int fstride) {
+  // FPB > 1 (the 32-thread class): FPB fronts per CTA, one warp each, warp-level barriers only
+  const int slot = (FPB > 1) ? (int)(threadIdx.x >> 5) : 0;
+  const int b = blockIdx.x * FPB + slot;
   if (b >= count) return;
   const int s = list[b];
-  B2_DYN_SMEM(raw);
+  B2_DYN_SMEM(raw0);
+  unsigned char* raw = raw0 + (size_t)slot * fstride;
   double* xs = reinterpret_cast<double*>(raw);
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int64_t r0 = P.rptr[s];
   const int m = (int)(P.rptr[s + 1] - r0);
   double* red = xs + m;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = (FPB > 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;
   const double* Lp = P.Lx + P.lptr[s];
   for (int i = tid; i < m; i += NT) xs[i] = (i < w) ? x[c0 + i] : x[P.rowidx[r0 + i]];
-  __syncthreads();
+  B2_FSYNC();
   const int nblk = (w + SNB - 1) / SNB;
   for (int bi = nblk - 1; bi >= 0; bi--) {
     const int jb = bi * SNB;
@@ -653,7 +732,7 @@ __global__ void __launch_bounds__(NT) k_bwd(PlanDev P, const int32_t* __restrict
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) red[k] = acc;
     }
-    __syncthreads();
+    B2_FSYNC();
     if (warp == 0) {
       double lcol[SNB];  // lcol[k] = L(jb+k, jb+lane), k > lane
       B2_UNROLL
@@ -668,7 +747,7 @@ __global__ void __launch_bounds__(NT) k_bwd(PlanDev P, const int32_t* __restrict
       }
       if (lane < nb) xs[jb + lane] = v;
     }
-    __syncthreads();
+    B2_FSYNC();
   }
   for (int i = tid; i < w; i += NT) x[c0 + i] = xs[i];
 }
