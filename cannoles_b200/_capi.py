@@ -34,7 +34,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "b2_last_error", "b2_version", "b2_device_count", "b2_analyze", "b2_factorize",
     "b2_refactorize_shift", "b2_solve", "b2_factorize_dev", "b2_solve_dev", "b2_register_host",
-    "b2_unregister_host", "b2_stats", "b2_last_timings", "b2_timer_start", "b2_timer_stop", "b2_last_sweeps", "b2_profile", "b2_get_perm", "b2_get_csc",
+    "b2_unregister_host", "b2_stats", "b2_last_timings", "b2_timer_start", "b2_timer_stop", "b2_last_sweeps", "b2_profile", "b2_front_sizes", "b2_get_perm", "b2_get_csc",
     "b2_get_nzval", "b2_get_d", "b2_set_option", "b2_free",
     "b2b_analyze", "b2b_factorize", "b2b_refactorize_shift", "b2b_solve", "b2b_factorize_dev",
     "b2b_solve_dev", "b2b_factor_solve", "b2b_factor_solve_dev", "b2b_stats", "b2b_last_ms",
@@ -61,6 +61,7 @@ def bind_library(path: str):
     lib.b2_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.b2_last_timings.argtypes = [vp, pd]
     lib.b2_last_sweeps.argtypes = [vp]
+    lib.b2_front_sizes.argtypes = [vp, C.c_int64, p32, p32, p32]
     lib.b2_profile.argtypes = [vp, C.c_int, C.c_int, pi, pi, pi, pd, pi]
     lib.b2_timer_start.argtypes = [vp]
     lib.b2_timer_stop.argtypes = [vp, pd]

@@ -1,5 +1,6 @@
 // capi.cu -- extern "C" surface declared in include/cannoles_b200.h (single-system verbs and
 // device utilities; the batched verbs live in batched.cu).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -55,6 +56,7 @@ int b2_analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* cols
   if (const char* e = getenv("B2_SMALL_MAX_M")) h->eng.small_max_m = atof(e);
   if (const char* e = getenv("B2_NO_GRAPH")) h->eng.use_graph = atoi(e) == 0;
   if (const char* e = getenv("B2_SOLVE_BIG_M")) h->eng.solve_big_m = atof(e);
+  if (const char* e = getenv("B2_TINY_MAX_M")) h->eng.tiny_max_m = std::min(8, atoi(e));
   if (h->eng.init(device)) {
     h->eng.destroy();
     delete h;
@@ -162,6 +164,17 @@ int b2_timer_stop(b2_handle* h, double* ms) {
 int b2_profile(b2_handle* h, int which, int max, int* kinds, int* cls, int* counts, double* ms, int* n) {
   if (!h || !kinds || !cls || !counts || !ms || !n) return fail("b2_profile: NULL argument");
   return h->eng.profile(which, max, kinds, cls, counts, ms, n);
+}
+
+int b2_front_sizes(const b2_handle* h, int64_t max, int32_t* width, int32_t* order, int32_t* level) {
+  if (!h || !width || !order || !level) return fail("b2_front_sizes: NULL argument");
+  const b2::Symbolic& S = h->eng.sym;
+  for (int64_t s = 0; s < S.nsuper && s < max; s++) {
+    width[s] = S.scol[s + 1] - S.scol[s];
+    order[s] = (int32_t)(S.rptr[s + 1] - S.rptr[s]);
+    level[s] = S.slevel[s];
+  }
+  return 0;
 }
 
 int b2_last_sweeps(const b2_handle* h) { return h ? h->eng.last_sweeps : -1; }

@@ -51,11 +51,16 @@ int Engine::build_plan() {
   auto front_m = [&](int s) { return (int)(S.rptr[s + 1] - S.rptr[s]); };
   auto front_w = [&](int s) { return (int)(S.scol[s + 1] - S.scol[s]); };
   for (int l = 0; l < S.nlevels; l++) {
-    std::vector<int32_t> small[4], large, sol[4], big;
+    std::vector<int32_t> small[4], large, sol[4], big, tiny[2];
     int small_mmax[4] = {0, 0, 0, 0}, sol_mmax[4] = {0, 0, 0, 0};
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; q++) {
       int s = S.level_sn[q];
       int m = front_m(s);
+      if (m <= tiny_max_m && m <= (int)small_max_m) {   // one thread per front, factorization and solves
+        tiny[m <= 4 ? 0 : 1].push_back(s);
+        n_small++;
+        continue;
+      }
       if (m <= (int)small_max_m) {
         int c = small_class(m);
         small[c].push_back(s);
@@ -72,6 +77,14 @@ int Engine::build_plan() {
         sol[c].push_back(s);
         sol_mmax[c] = std::max(sol_mmax[c], m);
       }
+    }
+    for (int c = 0; c < 2; c++) {
+      if (tiny[c].empty()) continue;
+      Launch L; L.kind = LK_FRONT_TINY; L.cls = c; L.off = (int64_t)items.size(); L.count = (int)tiny[c].size();
+      items.insert(items.end(), tiny[c].begin(), tiny[c].end());
+      fact_launches.push_back(L);
+      L.kind = LK_FWD_TINY; fwd_launches.push_back(L);
+      L.kind = LK_BWD_TINY; bwd_launches.push_back(L);
     }
     for (int c = 0; c < 4; c++) {
       if (!small[c].empty()) {
@@ -354,6 +367,18 @@ int Engine::launch_one(const Launch& L, int pass) {
       else if (L.cls == 1) { auto kfn = k_bwd<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, stream, plan, it, L.count, d_x, 0); }
       else if (L.cls == 2) { auto kfn = k_bwd<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, stream, plan, it, L.count, d_x, 0); }
       else { auto kfn = k_bwd<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, stream, plan, it, L.count, d_x, 0); }
+      break;
+    case LK_FRONT_TINY:
+      if (L.cls == 0) B2_LAUNCH(k_front_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, stream, plan, it, L.count);
+      else B2_LAUNCH(k_front_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count);
+      break;
+    case LK_FWD_TINY:
+      if (L.cls == 0) B2_LAUNCH(k_fwd_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, stream, plan, it, L.count, d_x, d_upd);
+      else B2_LAUNCH(k_fwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count, d_x, d_upd);
+      break;
+    case LK_BWD_TINY:
+      if (L.cls == 0) B2_LAUNCH(k_bwd_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, stream, plan, it, L.count, d_x);
+      else B2_LAUNCH(k_bwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count, d_x);
       break;
     case LK_FWD_BIG:
       B2_LAUNCH(k_fwd_big, L.count, 256, 0, stream, plan, it, L.count, d_x, d_upd, d_ypub, d_sflags);

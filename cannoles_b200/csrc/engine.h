@@ -19,6 +19,9 @@ enum LaunchKind : int {
   LK_BWD,
   LK_FWD_BIG,
   LK_BWD_BIG,
+  LK_FRONT_TINY,
+  LK_FWD_TINY,
+  LK_BWD_TINY,
 };
 
 struct Launch {
@@ -36,6 +39,7 @@ struct Engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   double small_max_m = 128;  // fronts up to this order take the shared-memory path
+  int tiny_max_m = 8;        // fronts up to this order (4 / 8 classes) take the one-thread-per-front kernels
   double solve_big_m = 384;  // fronts above this order take the multi-CTA solve kernels
 
   // device buffers

@@ -172,6 +172,57 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
 }
 
 // ------------------------------------------------------------------------------------------
+// (2a') tiny fronts (order <= MM, MM = 4 or 8): one THREAD per front.  Half of the fronts of a
+// KKT system are leaves of order 2-8 (an r_i or lambda_j with its few neighbours): a warp per
+// front leaves 31 lanes idle and is CTA-launch bound.  The front lives in a per-thread slice of
+// shared memory (element e of thread t at Fs[e * tiny_nt(MM) + t]: conflict-free), same steps as
+// k_front_small, no barriers.
+// ------------------------------------------------------------------------------------------
+template <int MM>
+__global__ void __launch_bounds__(tiny_nt(MM)) k_front_tiny(PlanDev P, const int32_t* __restrict__ list, int count) {
+  constexpr int TNT = tiny_nt(MM);
+  __shared__ double Fs[MM * MM * TNT];
+  const int b = blockIdx.x * TNT + threadIdx.x;
+  if (b >= count) return;
+  const int s = list[b];
+  double* F = Fs + threadIdx.x;
+  const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+  const int64_t r0 = P.rptr[s];
+  const int m = (int)(P.rptr[s + 1] - r0);
+  const int r = m - w;
+  for (int e = 0; e < m * m; e++) F[e * TNT] = 0.0;
+  for (int64_t q = P.amap_ptr[s]; q < P.amap_ptr[s + 1]; q++) F[P.amap_pos[q] * TNT] = P.nzval[P.amap_slot[q]];
+  for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
+    const int c = P.child_idx[ci];
+    const int wc = P.scol[c + 1] - P.scol[c];
+    const int64_t rc0 = P.rptr[c] + wc;
+    const int rc = (int)(P.rptr[c + 1] - rc0);
+    const int32_t* relc = P.rel + rc0;
+    const double* cb = P.CB + P.cbptr[c];
+    for (int j = 0; j < rc; j++) {
+      const int J = relc[j];
+      for (int i = j; i < rc; i++) F[(relc[i] + J * m) * TNT] += cb[i + (size_t)j * rc];
+    }
+  }
+  for (int k = 0; k < w; k++) {
+    const double dk = F[(k + k * m) * TNT];
+    P.dvec[c0 + k] = dk;
+    if (dk == 0.0) P.flags[0] = 1;
+    for (int j = k + 1; j < m; j++) {
+      const double lj = F[(j + k * m) * TNT] / dk;
+      for (int i = j; i < m; i++) F[(i + j * m) * TNT] -= F[(i + k * m) * TNT] * lj;   // column k still unscaled
+    }
+    for (int i = k + 1; i < m; i++) F[(i + k * m) * TNT] /= dk;
+  }
+  double* Lp = P.Lx + P.lptr[s];
+  for (int j = 0; j < w; j++)
+    for (int i = j; i < m; i++) Lp[i + j * m] = F[(i + j * m) * TNT];
+  double* cbp = P.CB + P.cbptr[s];
+  for (int j = 0; j < r; j++)
+    for (int i = j; i < r; i++) cbp[i + (size_t)j * r] = F[((w + i) + (w + j) * m) * TNT];
+}
+
+// ------------------------------------------------------------------------------------------
 // (2b) tiled path for fronts that do not fit in shared memory.  Pivot blocks of NB = TILE = 64
 // columns; per block: diagonal 64 x 64 LDL^T (inside the CTA that produced it) -> k_trsm
 // (rows below) -> k_update (trailing pivot columns, FP64 tensor-core tiles); one more k_update
@@ -255,24 +306,6 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
   }
 }
 
-// 1 / d to (nearly) full double precision on a SHORT dependent chain: FP32 reciprocal as the seed
-// (24 bits), two Newton steps in FP64 (4 dependent DFMAs instead of the ~8 of __drcp_rn).  The
-// reciprocal of a pivot sits on the critical path of every elimination step.
-__device__ __forceinline__ double fast_rcp(double d) {
-#ifdef B2_EMULATE
-  return 1.0 / d;
-#else
-  const double ad = fabs(d);
-  if (!(ad > 1e-30 && ad < 1e30)) return __drcp_rn(d);
-  double x = (double)__frcp_rn((float)d);
-  double e = __fma_rn(-d, x, 1.0);
-  x = __fma_rn(x, e, x);
-  e = __fma_rn(-d, x, 1.0);
-  x = __fma_rn(x, e, x);
-  return x;
-#endif
-}
-
 // CTA-level pivot-free LDL^T of an nb x nb block (nb <= NB = 64) held column-major in shared
 // memory (S[i + j * DIAG_LD], lower triangle), blocked in 8-column panels.  Panel step, warp 0:
 // EVERY lane factors the 8 x 8 diagonal sub-block redundantly in registers (no shuffles on the
@@ -300,7 +333,7 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
       B2_UNROLL
       for (int c = 0; c < 8; c++) {
         if (g[c][c] == 0.0) bad = 1;
-        rd[c] = fast_rcp(g[c][c]);
+        rd[c] = __drcp_rn(g[c][c]);
         B2_UNROLL
         for (int r = c + 1; r < 8; r++) {
           const double lrc = g[r][c] * rd[c];
@@ -750,6 +783,60 @@ __global__ void __launch_bounds__(NT * FPB) k_bwd(PlanDev P, const int32_t* __re
     B2_FSYNC();
   }
   for (int i = tid; i < w; i += NT) x[c0 + i] = xs[i];
+}
+
+// (3a') tiny fronts: one thread per front (see k_front_tiny)
+template <int MM>
+__global__ void __launch_bounds__(tiny_nt(MM)) k_fwd_tiny(PlanDev P, const int32_t* __restrict__ list, int count,
+                                                      double* __restrict__ x, double* __restrict__ upd) {
+  constexpr int TNT = tiny_nt(MM);
+  __shared__ double Xs[MM * TNT];
+  const int b = blockIdx.x * TNT + threadIdx.x;
+  if (b >= count) return;
+  const int s = list[b];
+  double* xs = Xs + threadIdx.x;
+  const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+  const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
+  const double* Lp = P.Lx + P.lptr[s];
+  for (int i = 0; i < m; i++) xs[i * TNT] = (i < w) ? x[c0 + i] : 0.0;
+  for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
+    const int c = P.child_idx[ci];
+    const int wc = P.scol[c + 1] - P.scol[c];
+    const int64_t rc0 = P.rptr[c] + wc;
+    const int rc = (int)(P.rptr[c + 1] - rc0);
+    const int32_t* relc = P.rel + rc0;
+    const double* uc = upd + P.uptr[c];
+    for (int k = 0; k < rc; k++) xs[relc[k] * TNT] += uc[k];
+  }
+  for (int j = 0; j < w; j++) {
+    const double yj = xs[j * TNT];
+    for (int i = j + 1; i < m; i++) xs[i * TNT] -= Lp[i + j * m] * yj;
+    x[c0 + j] = yj / P.dvec[c0 + j];
+  }
+  double* us = upd + P.uptr[s];
+  for (int i = w; i < m; i++) us[i - w] = xs[i * TNT];
+}
+
+template <int MM>
+__global__ void __launch_bounds__(tiny_nt(MM)) k_bwd_tiny(PlanDev P, const int32_t* __restrict__ list, int count,
+                                                      double* __restrict__ x) {
+  constexpr int TNT = tiny_nt(MM);
+  __shared__ double Xs[MM * TNT];
+  const int b = blockIdx.x * TNT + threadIdx.x;
+  if (b >= count) return;
+  const int s = list[b];
+  double* xs = Xs + threadIdx.x;
+  const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+  const int64_t r0 = P.rptr[s];
+  const int m = (int)(P.rptr[s + 1] - r0);
+  const double* Lp = P.Lx + P.lptr[s];
+  for (int i = 0; i < m; i++) xs[i * TNT] = (i < w) ? x[c0 + i] : x[P.rowidx[r0 + i]];
+  for (int j = w - 1; j >= 0; j--) {
+    double acc = xs[j * TNT];
+    for (int i = j + 1; i < m; i++) acc -= Lp[i + j * m] * xs[i * TNT];
+    xs[j * TNT] = acc;
+    x[c0 + j] = acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -38,6 +38,11 @@ constexpr int TRSM_THREADS = 128;
 constexpr int TRSM_ROWS = 256;  // rows of the panel per k_trsm CTA (two per thread)
 constexpr int ASM_COLS = 8;   // destination tile of k_assemble_large: ASM_ROWS x ASM_COLS
 constexpr int ASM_ROWS = 512;
+// threads (= fronts) per CTA of the one-thread-per-front kernels for fronts of order <= mm
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr int tiny_nt(int mm) { return mm <= 4 ? 128 : 64; }
 constexpr int FPB32 = 4;      // fronts per CTA in the 32-thread class of the per-front kernels (one warp each)
 constexpr int SNB = 32;       // column block of the one-CTA-per-front solve kernels
 constexpr int SB = 64;        // row chunk / column block of the multi-CTA solve of big fronts

@@ -110,6 +110,9 @@ int b2_stats(const b2_handle* h, b2_stats_t* out);
 /* device milliseconds of the phases of the last call: [0] upload, [1] COO->CSC assembly,
  * [2] numeric factorization (+ inertia), [3] solve (+ refinement), [4] download */
 int b2_last_timings(const b2_handle* h, double* ms5);
+/* pivot-block width, order (rows) and assembly-tree level of every front (supernode-size
+ * histogram for the roofline discussion); arrays of b2_stats().nsuper entries */
+int b2_front_sizes(const b2_handle* h, int64_t max, int32_t* width, int32_t* order, int32_t* level);
 /* Developer aid: replay the factorization (which = 0) or one forward+backward sweep
  * (which = 1) launch by launch outside the CUDA graph, an event after every launch; returns per
  * launch the kernel kind, its class / mode, the CTA count and the warm-cache device time. */
