@@ -51,7 +51,7 @@ int Engine::build_plan() {
   auto front_m = [&](int s) { return (int)(S.rptr[s + 1] - S.rptr[s]); };
   auto front_w = [&](int s) { return (int)(S.scol[s + 1] - S.scol[s]); };
   for (int l = 0; l < S.nlevels; l++) {
-    std::vector<int32_t> small[4], large, sol[4], big, tiny[2];
+    std::vector<int32_t> small[4], large, sol[4], big, tiny[2], tsol[2];
     int small_mmax[4] = {0, 0, 0, 0}, sol_mmax[4] = {0, 0, 0, 0};
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; q++) {
       int s = S.level_sn[q];
@@ -72,6 +72,8 @@ int Engine::build_plan() {
       }
       if (m > (int)solve_big_m) {
         big.push_back(s);
+      } else if (m <= tiny_solve_max_m) {
+        tsol[m <= 16 ? 0 : 1].push_back(s);
       } else {
         int c = solve_class(m);
         sol[c].push_back(s);
@@ -84,6 +86,13 @@ int Engine::build_plan() {
       items.insert(items.end(), tiny[c].begin(), tiny[c].end());
       fact_launches.push_back(L);
       L.kind = LK_FWD_TINY; fwd_launches.push_back(L);
+      L.kind = LK_BWD_TINY; bwd_launches.push_back(L);
+    }
+    for (int c = 0; c < 2; c++) {
+      if (tsol[c].empty()) continue;
+      Launch L; L.kind = LK_FWD_TINY; L.cls = 2 + c; L.off = (int64_t)items.size(); L.count = (int)tsol[c].size();
+      items.insert(items.end(), tsol[c].begin(), tsol[c].end());
+      fwd_launches.push_back(L);
       L.kind = LK_BWD_TINY; bwd_launches.push_back(L);
     }
     for (int c = 0; c < 4; c++) {
@@ -374,11 +383,15 @@ int Engine::launch_one(const Launch& L, int pass) {
       break;
     case LK_FWD_TINY:
       if (L.cls == 0) B2_LAUNCH(k_fwd_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, stream, plan, it, L.count, d_x, d_upd);
-      else B2_LAUNCH(k_fwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count, d_x, d_upd);
+      else if (L.cls == 1) B2_LAUNCH(k_fwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count, d_x, d_upd);
+      else if (L.cls == 2) B2_LAUNCH(k_fwd_tiny<16>, (L.count + tiny_nt(16) - 1) / tiny_nt(16), tiny_nt(16), 0, stream, plan, it, L.count, d_x, d_upd);
+      else B2_LAUNCH(k_fwd_tiny<32>, (L.count + tiny_nt(32) - 1) / tiny_nt(32), tiny_nt(32), 0, stream, plan, it, L.count, d_x, d_upd);
       break;
     case LK_BWD_TINY:
       if (L.cls == 0) B2_LAUNCH(k_bwd_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, stream, plan, it, L.count, d_x);
-      else B2_LAUNCH(k_bwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count, d_x);
+      else if (L.cls == 1) B2_LAUNCH(k_bwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count, d_x);
+      else if (L.cls == 2) B2_LAUNCH(k_bwd_tiny<16>, (L.count + tiny_nt(16) - 1) / tiny_nt(16), tiny_nt(16), 0, stream, plan, it, L.count, d_x);
+      else B2_LAUNCH(k_bwd_tiny<32>, (L.count + tiny_nt(32) - 1) / tiny_nt(32), tiny_nt(32), 0, stream, plan, it, L.count, d_x);
       break;
     case LK_FWD_BIG:
       B2_LAUNCH(k_fwd_big, L.count, 256, 0, stream, plan, it, L.count, d_x, d_upd, d_ypub, d_sflags);

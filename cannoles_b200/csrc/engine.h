@@ -38,9 +38,10 @@ struct Engine {
   Symbolic sym;
   int device = 0;
   cudaStream_t stream = nullptr;
-  double small_max_m = 128;  // fronts up to this order take the shared-memory path
+  double small_max_m = 72;   // fronts up to this order take the shared-memory path (measured: 72 beats 128 and 40 on C4)
   int tiny_max_m = 8;        // fronts up to this order (4 / 8 classes) take the one-thread-per-front kernels
-  double solve_big_m = 384;  // fronts above this order take the multi-CTA solve kernels
+  int tiny_solve_max_m = 32; // ... and up to this order (16 / 32 classes) in the solves only
+  double solve_big_m = 96;   // fronts above this order take the multi-CTA solve kernels (measured: 96 < 192 < 384)
 
   // device buffers
   int32_t *d_slot_ptr = nullptr, *d_coo_sorted = nullptr;
