@@ -44,6 +44,7 @@ int Engine::build_plan() {
   std::vector<int32_t> items;
   std::vector<int64_t> asm_cptr(1, 0);   // (tiled front, column block) -> children touching it
   std::vector<int32_t> asm_ent;
+  std::vector<int64_t> asm_off, sb_off;
   std::vector<int32_t> sb_ent, sb_flag(S.nsuper, 0);   // big-front solve: child entries, flag offsets
   nsflag = 0;
   fact_launches.clear(); fwd_launches.clear(); bwd_launches.clear();
@@ -137,9 +138,13 @@ int Engine::build_plan() {
           }
         }
         for (int c = 0; c < nblk + nbel; c++) {
-          int e0 = (int)(sb_ent.size() / 3);
-          sb_ent.insert(sb_ent.end(), bucket[c].begin(), bucket[c].end());
-          items.push_back(s); items.push_back(c); items.push_back(e0); items.push_back((int)(sb_ent.size() / 3));
+          int e0 = (int)(sb_ent.size() / 2);
+          for (size_t q = 0; q < bucket[c].size(); q += 3) {
+            int ch = bucket[c][q];
+            sb_ent.push_back(bucket[c][q + 1]); sb_ent.push_back(bucket[c][q + 2]);
+            sb_off.push_back(S.rptr[ch] + front_w(ch)); sb_off.push_back(S.uptr[ch]);
+          }
+          items.push_back(s); items.push_back(c); items.push_back(e0); items.push_back((int)(sb_ent.size() / 2));
           F.count++;
         }
       }
@@ -174,15 +179,33 @@ int Engine::build_plan() {
           }
         }
         for (int cb = 0; cb < ncb; cb++) {
-          asm_ent.insert(asm_ent.end(), bucket[cb].begin(), bucket[cb].end());
-          asm_cptr.push_back((int64_t)asm_ent.size() / 3);
+          for (size_t q = 0; q < bucket[cb].size(); q += 3) {
+            int ch = bucket[cb][q];
+            int wch = front_w(ch);
+            asm_ent.push_back(bucket[cb][q + 1]); asm_ent.push_back(bucket[cb][q + 2]);
+            asm_ent.push_back(front_m(ch) - wch); asm_ent.push_back(0);
+            asm_off.push_back(S.rptr[ch] + wch); asm_off.push_back(S.cbptr[ch]);
+          }
+          asm_cptr.push_back((int64_t)asm_ent.size() / 4);
         }
-        for (int cb = 0; cb < ncb; cb++)
+        const int32_t* apos = S.amap_pos.data() + S.amap_ptr[s];
+        const int64_t na = S.amap_ptr[s + 1] - S.amap_ptr[s];
+        const int w = front_w(s);
+        for (int cb = 0; cb < ncb; cb++) {
+          // A entries of pivot columns [j0, min(je, w)): positions row + col * m, sorted
+          int j0 = cb * ASM_COLS, je = std::min(j0 + ASM_COLS, m);
+          int qa = 0, qb = 0;
+          if (j0 < w) {
+            qa = (int)(std::lower_bound(apos, apos + na, j0 * m) - apos);
+            qb = (int)(std::lower_bound(apos, apos + na, std::min(je, w) * m) - apos);
+          }
           for (int rb = 0; rb < nrb; rb++) {
             if ((rb + 1) * ASM_ROWS <= cb * ASM_COLS) continue;   // tile entirely above the diagonal
             items.push_back(s); items.push_back(cb); items.push_back(rb); items.push_back(gbase + cb);
+            items.push_back(qa); items.push_back(qb);
             L.count++;
           }
+        }
       }
       fact_launches.push_back(L);
     }
@@ -247,7 +270,9 @@ int Engine::build_plan() {
   }
   if (upload(&d_asm_cptr, asm_cptr, bytes_device)) return -1;
   if (upload(&d_asm_ent, asm_ent, bytes_device)) return -1;
-  plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent;
+  if (upload(&d_asm_off, asm_off, bytes_device)) return -1;
+  if (upload(&d_sb_off, sb_off, bytes_device)) return -1;
+  plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent; plan.asm_off = d_asm_off; plan.sb_off = d_sb_off;
   if (upload(&d_sb_ent, sb_ent, bytes_device)) return -1;
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
   if (dalloc(&d_sflags, (size_t)(2 * nsflag), bytes_device)) return -1;
@@ -335,7 +360,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_sb_ent, d_sb_flag, d_sflags, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_off, d_sb_off, d_sb_ent, d_sb_flag, d_sflags, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);

@@ -40,7 +40,7 @@ struct Engine {
   cudaStream_t stream = nullptr;
   double small_max_m = 72;   // fronts up to this order take the shared-memory path (measured: 72 beats 128 and 40 on C4)
   int tiny_max_m = 8;        // fronts up to this order (4 / 8 classes) take the one-thread-per-front kernels
-  int tiny_solve_max_m = 32; // ... and up to this order (16 / 32 classes) in the solves only
+  int tiny_solve_max_m = 16; // ... and up to this order (16 / 32 classes) in the solves only (measured: 32 loses to a warp per front)
   double solve_big_m = 96;   // fronts above this order take the multi-CTA solve kernels (measured: 96 < 192 < 384)
 
   // device buffers
@@ -53,7 +53,7 @@ struct Engine {
   int64_t *d_rptr = nullptr, *d_lptr = nullptr, *d_cbptr = nullptr, *d_uptr = nullptr,
           *d_amap_ptr = nullptr;
   double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr, *d_dstage = nullptr;
-  int64_t *d_dsptr = nullptr, *d_asm_cptr = nullptr;
+  int64_t *d_dsptr = nullptr, *d_asm_cptr = nullptr, *d_asm_off = nullptr, *d_sb_off = nullptr;
   int32_t *d_asm_ent = nullptr, *d_sb_ent = nullptr, *d_sb_flag = nullptr;
   int* d_sflags = nullptr;     // block flags of the big-front solves: [0, nsflag) forward, [nsflag, 2 nsflag) backward
   int64_t nsflag = 0;

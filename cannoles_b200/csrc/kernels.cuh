@@ -229,19 +229,21 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_front_tiny(PlanDev P, const int
 // pass with K = w forms the contribution block.
 // ------------------------------------------------------------------------------------------
 
-// item = (front, destination column block, destination row chunk, global column-block id).
+// item = (front, destination column block, destination row chunk, global column-block id,
+// first / end A entry of the tile's columns relative to amap_ptr[front]).
 // The CTA owns the ASM_ROWS x ASM_COLS destination tile in shared memory: zero, scatter the A
 // entries of its columns, add the children's contribution blocks one child after the other
 // (fixed order => deterministic sums, no atomics), then write the tile once (panel columns j < w
 // go to Lx, the others to CB; only rows >= column are produced).  Which children touch a column
-// block, and with which of their columns, is precomputed on the host (asm_cptr / asm_ent): a
+// block, with which of their columns and where their data lives is precomputed on the host
+// (asm_cptr / asm_ent / asm_off, no dependent pointer chasing on the device): a
 // front at the top of the tree has hundreds of small children and scanning them all per tile
 // was the whole cost of this kernel.
 __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t* __restrict__ items, int nitems) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
-  const int s = items[4 * b], j0 = items[4 * b + 1] * ASM_COLS, i0 = items[4 * b + 2] * ASM_ROWS;
-  const int gcb = items[4 * b + 3];
+  const int s = items[6 * b], j0 = items[6 * b + 1] * ASM_COLS, i0 = items[6 * b + 2] * ASM_ROWS;
+  const int gcb = items[6 * b + 3];
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int64_t r0 = P.rptr[s];
   const int m = (int)(P.rptr[s + 1] - r0);
@@ -251,15 +253,9 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < ASM_COLS * ASM_ROWS; idx += 256) (&T[0][0])[idx] = 0.0;
   __syncthreads();
-  if (j0 < w) {  // A entries only land in pivot columns; amap is sorted by position
-    const int64_t a0 = P.amap_ptr[s], a1 = P.amap_ptr[s + 1];
-    const int lo_pos = j0 * m, hi_pos = min(je, w) * m;
-    int64_t lo = a0, hi = a1;
-    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (P.amap_pos[mid] < lo_pos) lo = mid + 1; else hi = mid; }
-    const int64_t qa = lo;
-    hi = a1;
-    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (P.amap_pos[mid] < hi_pos) lo = mid + 1; else hi = mid; }
-    const int64_t qb = lo;
+  {  // A entries of the tile's pivot columns: range precomputed on the host (amap is sorted by position)
+    const int64_t a0 = P.amap_ptr[s];
+    const int64_t qa = a0 + items[6 * b + 4], qb = a0 + items[6 * b + 5];
     for (int64_t q = qa + tid; q < qb; q += 256) {
       const int pos = P.amap_pos[q];
       const int j = pos / m, i = pos - j * m;
@@ -269,12 +265,9 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
   __syncthreads();
   const bool one_chunk = m <= ASM_ROWS;
   for (int64_t e = P.asm_cptr[gcb]; e < P.asm_cptr[gcb + 1]; e++) {
-    const int c = P.asm_ent[3 * e], ja = P.asm_ent[3 * e + 1], jz = P.asm_ent[3 * e + 2];
-    const int wc = P.scol[c + 1] - P.scol[c];
-    const int64_t rc0 = P.rptr[c] + wc;
-    const int rc = (int)(P.rptr[c + 1] - rc0);
-    const int32_t* relc = P.rel + rc0;
-    const double* cb = P.CB + P.cbptr[c];
+    const int ja = P.asm_ent[4 * e], jz = P.asm_ent[4 * e + 1], rc = P.asm_ent[4 * e + 2];
+    const int32_t* relc = P.rel + P.asm_off[2 * e];
+    const double* cb = P.CB + P.asm_off[2 * e + 1];
     int ia = ja, iz = rc;   // rows >= column, so the row range starts no earlier than ja
     if (!one_chunk) {
       int lo = ja, hi = rc;
@@ -870,7 +863,7 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 
 // item = (front, chunk, first entry, end entry): chunk c < nblk owns pivot rows
 // [64c, min(64c+64, w)); chunk c >= nblk owns the rows [w + 64(c-nblk), ...) below the pivots.
-// entries (sb_ent triplets: child, first child row, end child row) list the child update vectors
+// entries (sb_ent: first / end child row; sb_off: offsets of the child's rel and update vector) list the child update vectors
 // that land in the chunk, in child order.
 __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __restrict__ items, int nitems,
                                                  double* __restrict__ x, double* __restrict__ upd,
@@ -893,10 +886,9 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
   if (tid < SB) t[tid] = (pivot && tid < nrow) ? x[c0 + i0 + tid] : 0.0;
   __syncthreads();
   for (int e = items[4 * b + 2]; e < items[4 * b + 3]; e++) {
-    const int ch = P.sb_ent[3 * e], ka = P.sb_ent[3 * e + 1], kz = P.sb_ent[3 * e + 2];
-    const int wc = P.scol[ch + 1] - P.scol[ch];
-    const int32_t* relc = P.rel + P.rptr[ch] + wc;
-    const double* uc = upd + P.uptr[ch];
+    const int ka = P.sb_ent[2 * e], kz = P.sb_ent[2 * e + 1];
+    const int32_t* relc = P.rel + P.sb_off[2 * e];
+    const double* uc = upd + P.sb_off[2 * e + 1];
     for (int k = ka + tid; k < kz; k += 256) t[relc[k] - i0] += uc[k];
     __syncthreads();
   }

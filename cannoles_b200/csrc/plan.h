@@ -24,8 +24,10 @@ struct PlanDev {
   double* dstage;         // factored diagonal blocks of the tiled fronts (NB x NB each)
   const int64_t* dsptr;   // per front: offset into dstage (tiled fronts only)
   const int64_t* asm_cptr; // per (tiled front, destination column block): range in asm_ent
-  const int32_t* asm_ent;  // triplets (child, first child column, end child column)
-  const int32_t* sb_ent;   // big-front solve: triplets (child, first child row, end child row)
+  const int32_t* asm_ent;  // per entry: first child column, end child column, child rows below, pad
+  const int64_t* asm_off;  // per entry: offset of the child's rel[] and of its contribution block
+  const int32_t* sb_ent;   // big-front solve, per entry: first child row, end child row
+  const int64_t* sb_off;   // per entry: offset of the child's rel[] and of its update vector
   const int32_t* sb_flag;  // per front: offset of its block flags (big fronts only)
   int* flags;  // [0] = breakdown (exact zero pivot seen)
 };
@@ -37,7 +39,7 @@ constexpr int DIAG_LD = 65;   // leading dimension of a diagonal block in shared
 constexpr int TRSM_THREADS = 128;
 constexpr int TRSM_ROWS = 256;  // rows of the panel per k_trsm CTA (two per thread)
 constexpr int ASM_COLS = 8;   // destination tile of k_assemble_large: ASM_ROWS x ASM_COLS
-constexpr int ASM_ROWS = 512;
+constexpr int ASM_ROWS = 256;
 // threads (= fronts) per CTA of the one-thread-per-front kernels for fronts of order <= mm
 #ifdef __CUDACC__
 __host__ __device__
