@@ -199,6 +199,12 @@ int failb(const char* msg) {
 }
 }  // namespace
 
+#ifdef B2_TIMING
+extern "C" int b2b_debug_clocks(long long* out64) {
+  return cudaMemcpyFromSymbol(out64, b2::b2_dbg, 64 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" {
 
 int b2b_analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* cols1, int64_t nvar,

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   const int N = P.N;
   if (tid < 4) cnt[tid] = 0;
 
+  B2_TICK(30);
   if (flags & BF_LOAD) {
     const double* src = Lout + (size_t)b * P.npacked;
     for (int i = tid; i < P.npacked; i += NT) Pk[i] = src[i];
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
       Pk[P.multi_dst[q]] = acc;
     }
     __syncthreads();
+    B2_TICK(31);
     // ---------------------------------------------------------------- factorize
     for (int ph = 0; ph < P.nphase; ph++) {
       // (a) left-looking update of every panel of this level, 8 x 8 tiles on the tensor cores
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
         }
       }
       __syncthreads();
+      B2_TICK(32 + 2 * ph);
       // (b) dense factorization of every panel of this level
       //     width-1 supernodes: all in parallel (one scaling per row); wider ones: column loop
       for (int qs = P.ph_ptr[ph] + warp; qs < P.ph_ptr[ph + 1]; qs += NW) {
@@ -183,7 +186,9 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
         }
       }
       __syncthreads();
+      B2_TICK(33 + 2 * ph);
     }
+    B2_TICK(40);
     // ---------------------------------------------------------------- inertia
     {
       int pos = 0, zer = 0, neg = 0, brk = 0;
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
     if ((flags & BF_SOLVE) && !(cnt[0] == P.nvar && cnt[1] == 0)) return;  // wrong inertia: no solve
   }
   if (!(flags & BF_SOLVE)) return;
+  B2_TICK(41);
   // ------------------------------------------------------------------ solve (factor in smem)
   const double* bvec = rhs + (size_t)b * N;
   for (int k = tid; k < N; k += NT) xs[k] = bvec[P.perm[k]];
@@ -281,6 +287,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   const double sign = (flags & BF_NEGATE) ? -1.0 : 1.0;
   double* dv = dout + (size_t)b * N;
   for (int k = tid; k < N; k += NT) dv[P.perm[k]] = sign * xs[k];
+  B2_TICK(42);
 }
 
 }  // namespace b2

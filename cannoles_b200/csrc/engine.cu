@@ -162,7 +162,8 @@ int Engine::build_plan() {
       Launch L; L.kind = LK_ASSEMBLE_LARGE; L.off = (int64_t)items.size();
       for (int s : large) {
         int m = front_m(s);
-        int ncb = (m + ASM_COLS - 1) / ASM_COLS, nrb = (m + ASM_ROWS - 1) / ASM_ROWS;
+        const int acols = m <= 128 ? 16 : 8, arows = ASM_TILE / acols;   // tile shape of this front
+        int ncb = (m + acols - 1) / acols, nrb = (m + arows - 1) / arows;
         // children (ascending, the extend-add order) bucketed by the column blocks they touch
         const int gbase = (int)asm_cptr.size() - 1;
         std::vector<std::vector<int32_t>> bucket(ncb);
@@ -173,8 +174,8 @@ int Engine::build_plan() {
           int rc = front_m(c) - wc;
           int j = 0;
           while (j < rc) {
-            int blk = relc[j] / ASM_COLS, ja = j;
-            while (j < rc && relc[j] / ASM_COLS == blk) j++;
+            int blk = relc[j] / acols, ja = j;
+            while (j < rc && relc[j] / acols == blk) j++;
             bucket[blk].push_back(c); bucket[blk].push_back(ja); bucket[blk].push_back(j);
           }
         }
@@ -193,16 +194,16 @@ int Engine::build_plan() {
         const int w = front_w(s);
         for (int cb = 0; cb < ncb; cb++) {
           // A entries of pivot columns [j0, min(je, w)): positions row + col * m, sorted
-          int j0 = cb * ASM_COLS, je = std::min(j0 + ASM_COLS, m);
+          int j0 = cb * acols, je = std::min(j0 + acols, m);
           int qa = 0, qb = 0;
           if (j0 < w) {
             qa = (int)(std::lower_bound(apos, apos + na, j0 * m) - apos);
             qb = (int)(std::lower_bound(apos, apos + na, std::min(je, w) * m) - apos);
           }
           for (int rb = 0; rb < nrb; rb++) {
-            if ((rb + 1) * ASM_ROWS <= cb * ASM_COLS) continue;   // tile entirely above the diagonal
-            items.push_back(s); items.push_back(cb); items.push_back(rb); items.push_back(gbase + cb);
-            items.push_back(qa); items.push_back(qb);
+            if ((rb + 1) * arows <= cb * acols) continue;   // tile entirely above the diagonal
+            items.push_back(s); items.push_back(j0); items.push_back(rb * arows); items.push_back(gbase + cb);
+            items.push_back(qa); items.push_back(qb); items.push_back(acols); items.push_back(arows);
             L.count++;
           }
         }

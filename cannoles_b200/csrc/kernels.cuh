@@ -23,14 +23,6 @@ namespace b2 {
 // barrier of the threads that share one front: the whole CTA, or one warp when FPB fronts share a CTA
 #define B2_FSYNC() do { if (FPB > 1) __syncwarp(); else __syncthreads(); } while (0)
 
-#ifdef B2_TIMING
-__device__ long long b2_dbg[64];
-#define B2_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] = clock64(); } while (0)
-#define B2_ACC(i, t0) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] += clock64() - (t0); } while (0)
-#else
-#define B2_TICK(i)
-#define B2_ACC(i, t0)
-#endif
 
 // ------------------------------------------------------------------------------------------
 // (1) COO -> CSC.  One thread per CSC slot; the duplicates of a slot are summed in increasing
@@ -229,9 +221,10 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_front_tiny(PlanDev P, const int
 // pass with K = w forms the contribution block.
 // ------------------------------------------------------------------------------------------
 
-// item = (front, destination column block, destination row chunk, global column-block id,
-// first / end A entry of the tile's columns relative to amap_ptr[front]).
-// The CTA owns the ASM_ROWS x ASM_COLS destination tile in shared memory: zero, scatter the A
+// item = (front, first destination column, first destination row, global column-block id,
+// first / end A entry of the tile's columns relative to amap_ptr[front], tile columns, tile rows).
+// The CTA owns an nrows x ncols destination tile in shared memory (16 x 128 for fronts of order
+// <= 128, 8 x 256 above): zero, scatter the A
 // entries of its columns, add the children's contribution blocks one child after the other
 // (fixed order => deterministic sums, no atomics), then write the tile once (panel columns j < w
 // go to Lx, the others to CB; only rows >= column are produced).  Which children touch a column
@@ -242,55 +235,62 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_front_tiny(PlanDev P, const int
 __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t* __restrict__ items, int nitems) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
-  const int s = items[6 * b], j0 = items[6 * b + 1] * ASM_COLS, i0 = items[6 * b + 2] * ASM_ROWS;
-  const int gcb = items[6 * b + 3];
+  const int s = items[8 * b], j0 = items[8 * b + 1], i0 = items[8 * b + 2];
+  const int gcb = items[8 * b + 3];
+  const int ncols = items[8 * b + 6], nrows = items[8 * b + 7];   // tile shape: ncols * nrows <= ASM_TILE
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int64_t r0 = P.rptr[s];
   const int m = (int)(P.rptr[s + 1] - r0);
   const int r = m - w;
-  const int je = min(j0 + ASM_COLS, m), ie = min(i0 + ASM_ROWS, m);
-  __shared__ double T[ASM_COLS][ASM_ROWS];
+  const int je = min(j0 + ncols, m), ie = min(i0 + nrows, m);
+  __shared__ double T[ASM_TILE];   // T[(j - j0) * nrows + (i - i0)]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int idx = tid; idx < ASM_COLS * ASM_ROWS; idx += 256) (&T[0][0])[idx] = 0.0;
+  for (int idx = tid; idx < ncols * nrows; idx += 256) T[idx] = 0.0;
   __syncthreads();
   {  // A entries of the tile's pivot columns: range precomputed on the host (amap is sorted by position)
     const int64_t a0 = P.amap_ptr[s];
-    const int64_t qa = a0 + items[6 * b + 4], qb = a0 + items[6 * b + 5];
+    const int64_t qa = a0 + items[8 * b + 4], qb = a0 + items[8 * b + 5];
     for (int64_t q = qa + tid; q < qb; q += 256) {
       const int pos = P.amap_pos[q];
       const int j = pos / m, i = pos - j * m;
-      if (i >= i0 && i < ie) T[j - j0][i - i0] = P.nzval[P.amap_slot[q]];
+      if (i >= i0 && i < ie) T[(j - j0) * nrows + (i - i0)] = P.nzval[P.amap_slot[q]];
     }
   }
   __syncthreads();
-  const bool one_chunk = m <= ASM_ROWS;
+  // Every warp owns the destination columns j0 + warp, j0 + warp + 8 (< je) of the tile and walks
+  // the child entries on its own: a child maps at most one of its columns onto a destination
+  // column, the children are visited in order (deterministic sums) and no barrier is needed
+  // between them because no two warps touch the same column of T.
+  const bool one_chunk = m <= nrows;
   for (int64_t e = P.asm_cptr[gcb]; e < P.asm_cptr[gcb + 1]; e++) {
     const int ja = P.asm_ent[4 * e], jz = P.asm_ent[4 * e + 1], rc = P.asm_ent[4 * e + 2];
     const int32_t* relc = P.rel + P.asm_off[2 * e];
     const double* cb = P.CB + P.asm_off[2 * e + 1];
-    int ia = ja, iz = rc;   // rows >= column, so the row range starts no earlier than ja
-    if (!one_chunk) {
-      int lo = ja, hi = rc;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < i0) lo = mid + 1; else hi = mid; }
-      ia = lo;
-      hi = rc;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < ie) lo = mid + 1; else hi = mid; }
-      iz = lo;
-    }
-    if (ia < iz) {   // uniform over the CTA
-      for (int j = ja + warp; j < jz; j += 8) {
-        double* dst = &T[relc[j] - j0][0] - i0;
-        const double* src = cb + (size_t)j * rc;
-#pragma unroll 4
-        for (int i = max(ia, j) + lane; i < iz; i += 32) dst[relc[i]] += src[i];
+    const int myrel = (ja + lane < jz) ? relc[ja + lane] : -1;   // jz - ja <= ncols <= 16
+    for (int J = j0 + warp; J < je; J += 8) {
+      const unsigned hit = __ballot_sync(0xffffffffu, myrel == J);
+      if (hit == 0) continue;
+      const int j = ja + __ffs(hit) - 1;
+      int ia = j, iz = rc;   // rows >= column
+      if (!one_chunk) {
+        int lo = j, hi = rc;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < i0) lo = mid + 1; else hi = mid; }
+        ia = lo;
+        hi = rc;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < ie) lo = mid + 1; else hi = mid; }
+        iz = lo;
       }
-      __syncthreads();
+      double* dst = T + (J - j0) * nrows - i0;
+      const double* src = cb + (size_t)j * rc;
+#pragma unroll 4
+      for (int i = ia + lane; i < iz; i += 32) dst[relc[i]] += src[i];
     }
   }
+  __syncthreads();
   double* Lp = P.Lx + P.lptr[s];
   double* cbp = P.CB + P.cbptr[s];
   for (int j = j0 + warp; j < je; j += 8) {
-    const double* src = &T[j - j0][0] - i0;
+    const double* src = T + (j - j0) * nrows - i0;
     if (j < w) {
       for (int i = max(i0, j) + lane; i < ie; i += 32) Lp[i + (size_t)j * m] = src[i];
     } else {

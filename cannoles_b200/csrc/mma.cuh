@@ -4,6 +4,15 @@
 
 namespace b2 {
 
+#ifdef B2_TIMING
+__device__ long long b2_dbg[64];
+#define B2_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] = clock64(); } while (0)
+#define B2_ACC(i, t0) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] += clock64() - (t0); } while (0)
+#else
+#define B2_TICK(i)
+#define B2_ACC(i, t0)
+#endif
+
 // D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores (PTX mma.m8n8k4.f64 = SASS DMMA).
 // Fragments, g = lane/4, t = lane%4:  a = A[g][t], b = B[t][g], c0/c1 = C[g][2t + {0,1}].
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {

@@ -38,8 +38,7 @@ constexpr int UPD_KC = 16;    // K-chunk of k_update's shared-memory pipeline
 constexpr int DIAG_LD = 65;   // leading dimension of a diagonal block in shared memory
 constexpr int TRSM_THREADS = 128;
 constexpr int TRSM_ROWS = 256;  // rows of the panel per k_trsm CTA (two per thread)
-constexpr int ASM_COLS = 8;   // destination tile of k_assemble_large: ASM_ROWS x ASM_COLS
-constexpr int ASM_ROWS = 256;
+constexpr int ASM_TILE = 2048; // doubles in the destination tile of k_assemble_large (8 x 256 or 16 x 128)
 // threads (= fronts) per CTA of the one-thread-per-front kernels for fronts of order <= mm
 #ifdef __CUDACC__
 __host__ __device__

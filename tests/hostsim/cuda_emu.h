@@ -223,6 +223,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   }
   return r;
 }
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
