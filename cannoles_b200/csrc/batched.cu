@@ -73,7 +73,7 @@ int BatchEngine::init(int dev, int64_t nbatch) {
   for (auto& e : ev) B2_CUDA_OK(cudaEventCreate(&e));
   for (auto& e : tev) B2_CUDA_OK(cudaEventCreate(&e));
   const int64_t npacked = (int64_t)N * (N + 1) / 2;
-  smem = (int)((npacked + 2 * (int64_t)N) * sizeof(double));
+  smem = (int)batched_smem_bytes(N);
   if (smem > 227 * 1024 - 64) {
     snprintf(g_last_error, sizeof(g_last_error),
              "b2b_analyze: N = %d needs %d bytes of shared memory per instance (> 227 KB); use the "

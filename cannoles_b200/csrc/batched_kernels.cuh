@@ -4,12 +4,16 @@
 //
 // Per instance, fused in ONE kernel (no factor ever leaves the SM unless asked for):
 //   assemble   COO values -> packed lower triangle of P K P' (duplicates summed in COO order)
-//   factorize  level-phased LEFT-looking supernodal LDL^T without pivoting: for every supernode
-//              of a tree level, panel -= L(:,K) D(K) L(J,K)' over its contributing columns K
-//              (FP64 tensor-core tiles, mma.sync m8n8k4 = SASS DMMA), then the dense panel
-//              factorization; structural zeros stay exact zeros in the packed array
+//   factorize  level-phased LEFT-looking supernodal LDL^T without pivoting.  For every supernode
+//              of a tree level: (a) panel -= L(:,K) D(K) L(J,K)' over its contributing columns K,
+//              8 x 8 x 4 FP64 tensor-core tiles (mma.sync m8n8k4 = SASS DMMA), each warp a strip of
+//              up to four row tiles so that the B fragment is reused; (b) the dense panel
+//              factorization in 8-column blocks: every thread factors the 8 x 8 diagonal block
+//              redundantly in registers (one reciprocal per pivot, no communication on the pivot
+//              chain), substitutes its own row, then a rank-8 DMMA update of the remaining columns
 //   inertia    pivot-sign counts (src/solver_types.jl:90-96)
-//   solve      forward / diagonal / backward substitution on the shared-memory factor
+//   solve      forward / diagonal / backward substitution on the shared-memory factor, the dense
+//              pivot blocks again in 8-column blocks
 // Algorithmic bytes per instance: 8 nnz in (+ 8 N rhs) and 8 N out; flops: sum_j (c_j^2 + 3 c_j).
 #pragma once
 #include "b2_cuda.h"
@@ -36,10 +40,83 @@ struct BatchPlanDev {
   const int32_t* multi_coo;  // COO indices, ascending inside a slot
 };
 
+// shared memory of k_batched, in bytes, for a system of order N
+inline size_t batched_smem_bytes(int N) {
+  return ((size_t)N * (N + 1) / 2 + 11 * (size_t)N) * sizeof(double) + 3 * (size_t)N * sizeof(int32_t);
+}
+
 // flags: bit0 = write the packed factor to Lout, bit1 = solve with rhs -> dout (only if the
 // inertia is the expected one), bit2 = negate the solution (solve_ldl!'s sign flip),
 // bit3 = read the factor from Lout instead of factorizing (solve-only call)
 constexpr int BF_STORE = 1, BF_SOLVE = 2, BF_NEGATE = 4, BF_LOAD = 8;
+
+// C(t, j) -= sum_{q < K} A(t, q) B(j, q) for local columns j in [jbeg, jend) and local rows t in
+// [j, m) of one supernode panel, in 8 x 8 tiles; each warp takes strips of up to four row tiles.
+//   A(t, q) = Pk[abase[q] + rowmap[t]]
+//   B(j, q) = FROM_W ? Wd[j * 8 + q] : Pk[abase[q] + c0 + j] * dd[q]
+//   C(t, j) = Pk[cbm[c0 + j] + rowmap[t]]
+template <int NW, bool FROM_W>
+__device__ __forceinline__ void panel_update(double* Pk, const int32_t* cbm, const int32_t* rowmap,
+                                             const int32_t* abase, const double* dd, const double* Wd,
+                                             int c0, int jbeg, int jend, int m, int K, int warp, int lane) {
+  const int g = lane >> 2, t4 = lane & 3;
+  const int ntj = (jend - jbeg + 7) >> 3, nti = (m - jbeg + 7) >> 3;
+  int task = 0;
+  for (int tj = 0; tj < ntj; tj++) {
+    for (int ti0 = tj; ti0 < nti; ti0 += 4, task++) {
+      if (task % NW != warp) continue;
+      double acc[4][2];
+      B2_UNROLL
+      for (int a = 0; a < 4; a++) { acc[a][0] = 0.0; acc[a][1] = 0.0; }
+      const int jb = jbeg + tj * 8 + g;                 // B-fragment column (local)
+      int ra[4];
+      B2_UNROLL
+      for (int a = 0; a < 4; a++) {
+        const int tr = jbeg + (ti0 + a) * 8 + g;        // A-fragment row (local)
+        ra[a] = (ti0 + a < nti && tr < m) ? rowmap[tr] : -1;
+      }
+      for (int q0 = 0; q0 < K; q0 += 4) {
+        const int q = q0 + t4;
+        double bv = 0.0, av[4] = {0.0, 0.0, 0.0, 0.0};
+        if (q < K) {
+          const int base = abase[q];
+          if (jb < jend) bv = FROM_W ? Wd[jb * 8 + q] : Pk[base + c0 + jb] * dd[q];
+          B2_UNROLL
+          for (int a = 0; a < 4; a++)
+            if (ra[a] >= 0) av[a] = Pk[base + ra[a]];
+        }
+        B2_UNROLL
+        for (int a = 0; a < 4; a++) dmma_8x8x4(acc[a][0], acc[a][1], av[a], bv);
+      }
+      const int cj = jbeg + tj * 8 + 2 * t4;            // C-fragment columns cj, cj + 1 (local)
+      B2_UNROLL
+      for (int a = 0; a < 4; a++) {
+        const int tr = jbeg + (ti0 + a) * 8 + g;
+        if (ti0 + a >= nti || tr >= m) continue;
+        const int gr = rowmap[tr];
+        if (cj < jend && tr >= cj) Pk[cbm[c0 + cj] + gr] -= acc[a][0];
+        if (cj + 1 < jend && tr >= cj + 1) Pk[cbm[c0 + cj + 1] + gr] -= acc[a][1];
+      }
+    }
+  }
+}
+
+// Pivot-free LDL^T of an 8 x 8 block held by EVERY thread in registers (g[c][t], t <= c):
+// afterwards g[c][t] (t < c) = L, g[c][c] = d_c, rd[c] = 1 / d_c.
+__device__ __forceinline__ void ldlt8_regs(double (&g)[8][8], double (&rd)[8]) {
+  B2_UNROLL
+  for (int c = 0; c < 8; c++) {
+    rd[c] = __drcp_rn(g[c][c]);
+    B2_UNROLL
+    for (int r = c + 1; r < 8; r++) {
+      const double lrc = g[r][c] * rd[c];
+      B2_UNROLL
+      for (int t = c + 1; t <= r; t++) g[r][t] -= lrc * g[t][c];   // column c still unscaled
+    }
+    B2_UNROLL
+    for (int r = c + 1; r < 8; r++) g[r][c] *= rd[c];
+  }
+}
 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const double* __restrict__ vals,
@@ -52,17 +129,23 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   const int b = blockIdx.x;
   if (b >= batch) return;
   if (active && !active[b]) return;
+  const int N = P.N;
   B2_DYN_SMEM(raw);
   double* Pk = reinterpret_cast<double*>(raw);   // packed lower triangle
-  double* xs = Pk + P.npacked;                   // N: solve vector / column scratch
-  double* lk = xs + P.N;                         // N
+  double* xs = Pk + P.npacked;                   // N: solve vector
+  double* lk = xs + N;                           // N: scratch
+  double* Wd = lk + N;                           // N x 8: W = L D of the current 8-column block
+  double* dd = Wd + 8 * N;                       // N: pivots of the contributing columns
+  int32_t* abase = reinterpret_cast<int32_t*>(dd + N);   // N: packed base of the contributing columns
+  int32_t* rowmap = abase + N;                   // N: local row -> permuted index
+  int32_t* cbm = rowmap + N;                     // N: copy of P.cbm
   __shared__ int cnt[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;
-  const int N = P.N;
   if (tid < 4) cnt[tid] = 0;
-
+  for (int k = tid; k < N; k += NT) cbm[k] = P.cbm[k];
   B2_TICK(30);
+
   if (flags & BF_LOAD) {
     const double* src = Lout + (size_t)b * P.npacked;
     for (int i = tid; i < P.npacked; i += NT) Pk[i] = src[i];
@@ -73,22 +156,41 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
     __syncthreads();
     const double* v = vals + (size_t)b * P.nnz;
     const int t_rho = P.nnz - P.nvar, t_del = t_rho - P.ncon;
-    for (int t = tid; t < P.nnz; t += NT) {
-      const int dst = P.dst_single[t];
-      if (dst < 0) continue;
-      double val = v[t];
-      if (rho_over && t >= t_rho) val = rho_over[b];
-      else if (delta_over && t >= t_del && t < t_rho) val = -delta_over[b];
-      Pk[dst] = 0.0 + val;
+    const bool over = rho_over != nullptr || delta_over != nullptr;
+    const double rho_b = rho_over ? rho_over[b] : 0.0, mdel_b = delta_over ? -delta_over[b] : 0.0;
+    constexpr int U = 8;   // loads of U entries in flight per thread
+    for (int t0 = tid; t0 < P.nnz; t0 += NT * U) {
+      int dst[U];
+      double val[U];
+      B2_UNROLL
+      for (int u = 0; u < U; u++) {
+        const int t = t0 + u * NT;
+        dst[u] = t < P.nnz ? P.dst_single[t] : -1;
+        val[u] = t < P.nnz ? v[t] : 0.0;
+      }
+      B2_UNROLL
+      for (int u = 0; u < U; u++) {
+        const int t = t0 + u * NT;
+        if (dst[u] < 0) continue;
+        double x = val[u];
+        if (over) {
+          if (rho_over && t >= t_rho) x = rho_b;
+          else if (delta_over && t >= t_del && t < t_rho) x = mdel_b;
+        }
+        Pk[dst[u]] = 0.0 + x;
+      }
     }
     for (int q = tid; q < P.nmulti; q += NT) {
+      const int p0 = P.multi_ptr[q], p1 = P.multi_ptr[q + 1];
       double acc = 0.0;
-      for (int p = P.multi_ptr[q]; p < P.multi_ptr[q + 1]; p++) {
+      for (int p = p0; p < p1; p++) {
         const int t = P.multi_coo[p];
-        double val = v[t];
-        if (rho_over && t >= t_rho) val = rho_over[b];
-        else if (delta_over && t >= t_del && t < t_rho) val = -delta_over[b];
-        acc += val;
+        double x = v[t];
+        if (over) {
+          if (rho_over && t >= t_rho) x = rho_b;
+          else if (delta_over && t >= t_del && t < t_rho) x = mdel_b;
+        }
+        acc += x;
       }
       Pk[P.multi_dst[q]] = acc;
     }
@@ -96,96 +198,80 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
     B2_TICK(31);
     // ---------------------------------------------------------------- factorize
     for (int ph = 0; ph < P.nphase; ph++) {
-      // (a) left-looking update of every panel of this level, 8 x 8 tiles on the tensor cores
-      for (int qs = P.ph_ptr[ph]; qs < P.ph_ptr[ph + 1]; qs++) {
+      const int q0 = P.ph_ptr[ph], q1 = P.ph_ptr[ph + 1];
+      // width-1 supernodes without contributions (the leaves): one warp each, all in parallel
+      for (int qs = q0 + warp; qs < q1; qs += NW) {
         const int s = P.ph_sn[qs];
-        const int nct = P.ct_ptr[s + 1] - P.ct_ptr[s];
-        if (nct == 0) continue;
+        const int c0 = P.sc0[s];
+        if (P.sc0[s + 1] - c0 != 1 || P.ct_ptr[s + 1] != P.ct_ptr[s]) continue;
+        const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
+        const int32_t* rb = P.rb_idx + P.rb_ptr[s];
+        const int base = cbm[c0];
+        const double rdk = __drcp_rn(Pk[base + c0]);
+        for (int i = lane; i < nrb; i += 32) Pk[base + rb[i]] *= rdk;
+      }
+      __syncthreads();
+      B2_TICK(32 + 2 * ph);
+      // every other supernode of the level, one after the other, the whole CTA on each
+      for (int qs = q0; qs < q1; qs++) {
+        const int s = P.ph_sn[qs];
         const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
+        const int nct = P.ct_ptr[s + 1] - P.ct_ptr[s];
+        if (w == 1 && nct == 0) continue;
         const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
         const int m = w + nrb;
         const int32_t* rb = P.rb_idx + P.rb_ptr[s];
         const int32_t* ct = P.ct_col + P.ct_ptr[s];
-        const int ntj = (w + 7) >> 3, nti = (m + 7) >> 3;
-        const int ntiles = ntj * nti;
-        for (int tile = warp; tile < ntiles; tile += NW) {
-          const int tj = tile / nti, ti = tile - tj * nti;
-          if (ti < tj) continue;
-          // A fragment row (target row) and B fragment column (target column) of this lane
-          const int ar = ti * 8 + (lane >> 2);
-          const int grow = ar < w ? c0 + ar : (ar < m ? rb[ar - w] : -1);
-          const int bc = tj * 8 + (lane >> 2);
-          const int gcol = bc < w ? c0 + bc : -1;
-          double acc0 = 0.0, acc1 = 0.0;
-          for (int kk = 0; kk < nct; kk += 4) {
-            const int ki = kk + (lane & 3);
-            double a = 0.0, bb = 0.0;
-            if (ki < nct) {
-              const int k = ct[ki];
-              const int base = P.cbm[k];
-              if (grow >= 0) a = Pk[base + grow];
-              if (gcol >= 0) bb = Pk[base + gcol] * Pk[base + k];
-            }
-            dmma_8x8x4(acc0, acc1, a, bb);
-          }
-          // C fragment: row lane/4, columns 2*(lane%4) + {0,1}
-          const int cr = ti * 8 + (lane >> 2);
-          const int crow = cr < w ? c0 + cr : (cr < m ? rb[cr - w] : -1);
-          const int cc = tj * 8 + (lane & 3) * 2;
-          if (crow >= 0) {
-            if (cc < w && crow >= c0 + cc) Pk[P.cbm[c0 + cc] + crow] -= acc0;
-            if (cc + 1 < w && crow >= c0 + cc + 1) Pk[P.cbm[c0 + cc + 1] + crow] -= acc1;
-          }
+        for (int t = tid; t < m; t += NT) rowmap[t] = t < w ? c0 + t : rb[t - w];
+        for (int q = tid; q < nct; q += NT) {
+          const int k = ct[q];
+          abase[q] = cbm[k];
+          dd[q] = Pk[cbm[k] + k];
         }
-      }
-      __syncthreads();
-      B2_TICK(32 + 2 * ph);
-      // (b) dense factorization of every panel of this level
-      //     width-1 supernodes: all in parallel (one scaling per row); wider ones: column loop
-      for (int qs = P.ph_ptr[ph] + warp; qs < P.ph_ptr[ph + 1]; qs += NW) {
-        const int s = P.ph_sn[qs];
-        const int c0 = P.sc0[s];
-        if (P.sc0[s + 1] - c0 != 1) continue;
-        const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
-        const int32_t* rb = P.rb_idx + P.rb_ptr[s];
-        const int base = P.cbm[c0];
-        const double dk = Pk[base + c0];
-        for (int i = lane; i < nrb; i += 32) Pk[base + rb[i]] /= dk;
-      }
-      for (int qs = P.ph_ptr[ph]; qs < P.ph_ptr[ph + 1]; qs++) {
-        const int s = P.ph_sn[qs];
-        const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
-        if (w == 1) continue;
-        const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
-        const int m = w + nrb;
-        const int32_t* rb = P.rb_idx + P.rb_ptr[s];
         __syncthreads();
-        for (int k = 0; k < w; k++) {
-          const int gk = c0 + k;
-          const int base = P.cbm[gk];
-          const double dk = Pk[base + gk];
-          // rows below the pivot inside the front: local index t in (k, m)
-          for (int t = k + 1 + tid; t < m; t += NT) {
-            const int g = t < w ? c0 + t : rb[t - w];
-            const double a = Pk[base + g];
-            const double l = a / dk;
-            xs[t] = a;
-            lk[t] = l;
-            Pk[base + g] = l;
-          }
-          __syncthreads();
-          for (int j = k + 1 + warp; j < w; j += NW) {
-            const double ajk = xs[j];
-            const int bj = P.cbm[c0 + j];
-            for (int t = j + lane; t < m; t += 32) {
-              const int g = t < w ? c0 + t : rb[t - w];
-              Pk[bj + g] -= lk[t] * ajk;
+        // (a) left-looking update of the panel with its contributing columns
+        if (nct > 0)
+          panel_update<NW, false>(Pk, cbm, rowmap, abase, dd, Wd, c0, 0, w, m, nct, warp, lane);
+        __syncthreads();
+        // (b) dense factorization of the panel, 8 columns at a time
+        for (int kb = 0; kb < w; kb += 8) {
+          const int pw = min(8, w - kb);
+          double g[8][8], rd[8], wv[8];
+          B2_UNROLL
+          for (int c = 0; c < 8; c++)
+            B2_UNROLL
+            for (int t = 0; t <= c; t++)
+              g[c][t] = (c < pw) ? Pk[cbm[c0 + kb + t] + c0 + kb + c] : (c == t ? 1.0 : 0.0);
+          const int tr = kb + tid;                       // this thread's row of the panel (local)
+          const bool has = tr < m;
+          const int gr = has ? rowmap[tr] : 0;
+          B2_UNROLL
+          for (int c = 0; c < 8; c++)
+            wv[c] = (has && c < pw && (tr >= w || kb + c <= tr)) ? Pk[cbm[c0 + kb + c] + gr] : 0.0;
+          __syncthreads();                               // the unfactored block has been read by everyone
+          if (tid < 8) abase[tid] = tid < pw ? cbm[c0 + kb + tid] : 0;
+          ldlt8_regs(g, rd);
+          B2_UNROLL
+          for (int c = 1; c < 8; c++)
+            B2_UNROLL
+            for (int t = 0; t < c; t++) wv[c] -= wv[t] * g[c][t];
+          if (has) {
+            B2_UNROLL
+            for (int c = 0; c < 8; c++) {
+              if (c < pw) {
+                const int col = kb + c;
+                if (tr > col) Pk[cbm[c0 + col] + gr] = wv[c] * rd[c];
+                else if (tr == col) Pk[cbm[c0 + col] + gr] = g[c][c];
+              }
+              Wd[tr * 8 + c] = (c < pw && tr > kb + c) ? wv[c] : 0.0;
             }
           }
           __syncthreads();
+          if (kb + 8 < w)
+            panel_update<NW, true>(Pk, cbm, rowmap, abase, dd, Wd, c0, kb + 8, w, m, pw, warp, lane);
+          __syncthreads();
         }
       }
-      __syncthreads();
       B2_TICK(33 + 2 * ph);
     }
     B2_TICK(40);
@@ -193,7 +279,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
     {
       int pos = 0, zer = 0, neg = 0, brk = 0;
       for (int k = tid; k < N; k += NT) {
-        const double d = Pk[P.cbm[k] + k];
+        const double d = Pk[cbm[k] + k];
         pos += d > eig_tol;
         zer += fabs(d) <= eig_tol;
         neg += d < -eig_tol;
@@ -218,71 +304,129 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   const double* bvec = rhs + (size_t)b * N;
   for (int k = tid; k < N; k += NT) xs[k] = bvec[P.perm[k]];
   __syncthreads();
-  // forward: per level, gather the contributions of finished columns, then the pivot block
+  // forward: L y = b, level by level; a supernode first gathers the contributions of the
+  // finished columns it depends on, then solves its own unit-lower pivot block
   for (int ph = 0; ph < P.nphase; ph++) {
     for (int qs = P.ph_ptr[ph]; qs < P.ph_ptr[ph + 1]; qs++) {
       const int s = P.ph_sn[qs];
+      const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
       const int nct = P.ct_ptr[s + 1] - P.ct_ptr[s];
-      if (nct == 0) continue;
-      const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
+      if (w == 1 && nct == 0) continue;                  // a leaf: nothing to do going forward
       const int32_t* ct = P.ct_col + P.ct_ptr[s];
-      for (int j = tid; j < w; j += NT) {
-        const int g = c0 + j;
-        double acc = 0.0;
-        for (int q = 0; q < nct; q++) {
-          const int k = ct[q];
-          acc += Pk[P.cbm[k] + g] * xs[k];
+      for (int q = tid; q < nct; q += NT) {
+        const int k = ct[q];
+        abase[q] = cbm[k];
+        lk[q] = xs[k];
+      }
+      __syncthreads();
+      if (tid < w && nct > 0) {
+        const int gr = c0 + tid;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int q = 0;
+        for (; q + 3 < nct; q += 4) {
+          a0 += Pk[abase[q] + gr] * lk[q];
+          a1 += Pk[abase[q + 1] + gr] * lk[q + 1];
+          a2 += Pk[abase[q + 2] + gr] * lk[q + 2];
+          a3 += Pk[abase[q + 3] + gr] * lk[q + 3];
         }
-        lk[g] = acc;
+        for (; q < nct; q++) a0 += Pk[abase[q] + gr] * lk[q];
+        xs[gr] -= (a0 + a1) + (a2 + a3);
+      }
+      __syncthreads();
+      for (int kb = 0; kb + 1 < w; kb += 8) {            // unit-lower pivot block, 8 columns at a time
+        const int pw = min(8, w - kb);
+        double y[8];
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) y[c] = c < pw ? xs[c0 + kb + c] : 0.0;
+        B2_UNROLL
+        for (int c = 1; c < 8; c++)
+          B2_UNROLL
+          for (int t = 0; t < c; t++)
+            if (c < pw) y[c] -= Pk[cbm[c0 + kb + t] + c0 + kb + c] * y[t];
+        const int tr = kb + 8 + tid;
+        double acc = 0.0;
+        if (tr < w) {
+          B2_UNROLL
+          for (int c = 0; c < 8; c++)
+            if (c < pw) acc += Pk[cbm[c0 + kb + c] + c0 + tr] * y[c];
+        }
+        __syncthreads();                                 // everybody has read xs[c0 + kb ..]
+        if (tr < w) xs[c0 + tr] -= acc;
+        if (tid == 0) {
+          B2_UNROLL
+          for (int c = 0; c < 8; c++)
+            if (c < pw) xs[c0 + kb + c] = y[c];
+        }
+        __syncthreads();
       }
     }
-    __syncthreads();
-    for (int qs = P.ph_ptr[ph]; qs < P.ph_ptr[ph + 1]; qs++) {
-      const int s = P.ph_sn[qs];
-      if (P.ct_ptr[s + 1] == P.ct_ptr[s]) continue;
-      const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
-      for (int j = tid; j < w; j += NT) xs[c0 + j] -= lk[c0 + j];
-    }
-    __syncthreads();
-    // unit-lower pivot blocks: one warp per supernode, columns in order
-    for (int qs = P.ph_ptr[ph] + warp; qs < P.ph_ptr[ph + 1]; qs += NW) {
-      const int s = P.ph_sn[qs];
-      const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
-      for (int k = 0; k + 1 < w; k++) {
-        const double yk = xs[c0 + k];
-        const int base = P.cbm[c0 + k];
-        for (int i = k + 1 + lane; i < w; i += 32) xs[c0 + i] -= Pk[base + c0 + i] * yk;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
   }
-  for (int k = tid; k < N; k += NT) xs[k] /= Pk[P.cbm[k] + k];
+  for (int k = tid; k < N; k += NT) xs[k] /= Pk[cbm[k] + k];
   __syncthreads();
-  // backward: levels in reverse; pivot block first, then nothing else is needed because the
-  // rows below a supernode belong to higher levels and are already final
+  // backward: L' x = z, levels in reverse; the rows below a supernode belong to higher levels
+  // and are already final
   for (int ph = P.nphase - 1; ph >= 0; ph--) {
-    for (int qs = P.ph_ptr[ph] + warp; qs < P.ph_ptr[ph + 1]; qs += NW) {
+    const int q0 = P.ph_ptr[ph], q1 = P.ph_ptr[ph + 1];
+    // rows below: width-1 supernodes one warp each (lanes over the rows, shuffle reduction)
+    for (int qs = q0 + warp; qs < q1; qs += NW) {
       const int s = P.ph_sn[qs];
-      const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
+      const int c0 = P.sc0[s];
+      if (P.sc0[s + 1] - c0 != 1) continue;
       const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
       const int32_t* rb = P.rb_idx + P.rb_ptr[s];
-      // x_k -= sum_{i in rows below} L(i,k) x_i   (one lane per column, rows sequential)
-      for (int j = lane; j < w; j += 32) {
-        const int base = P.cbm[c0 + j];
-        double acc = 0.0;
-        for (int i = 0; i < nrb; i++) acc += Pk[base + rb[i]] * xs[rb[i]];
-        xs[c0 + j] -= acc;
-      }
-      __syncwarp();
-      for (int k = w - 1; k > 0; k--) {
-        const double xk = xs[c0 + k];
-        // x_j -= L(k, j) x_k for j < k
-        for (int j = lane; j < k; j += 32) xs[c0 + j] -= Pk[P.cbm[c0 + j] + c0 + k] * xk;
-        __syncwarp();
-      }
+      const int base = cbm[c0];
+      double acc = 0.0;
+      for (int i = lane; i < nrb; i += 32) acc += Pk[base + rb[i]] * xs[rb[i]];
+      B2_UNROLL
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) xs[c0] -= acc;
     }
     __syncthreads();
+    for (int qs = q0; qs < q1; qs++) {
+      const int s = P.ph_sn[qs];
+      const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
+      if (w == 1) continue;
+      const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
+      const int32_t* rb = P.rb_idx + P.rb_ptr[s];
+      if (tid < w && nrb > 0) {                          // one thread per column over the rows below
+        const int base = cbm[c0 + tid];
+        double a0 = 0.0, a1 = 0.0;
+        int i = 0;
+        for (; i + 1 < nrb; i += 2) {
+          a0 += Pk[base + rb[i]] * xs[rb[i]];
+          a1 += Pk[base + rb[i + 1]] * xs[rb[i + 1]];
+        }
+        if (i < nrb) a0 += Pk[base + rb[i]] * xs[rb[i]];
+        xs[c0 + tid] -= a0 + a1;
+      }
+      __syncthreads();
+      for (int kb = ((w - 1) >> 3) << 3; kb >= 0; kb -= 8) {   // L11' x = z, 8 columns at a time from the end
+        const int pw = min(8, w - kb);
+        double x8[8];
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) x8[c] = c < pw ? xs[c0 + kb + c] : 0.0;
+        B2_UNROLL
+        for (int c = 6; c >= 0; c--)
+          B2_UNROLL
+          for (int t = c + 1; t < 8; t++)
+            if (t < pw) x8[c] -= Pk[cbm[c0 + kb + c] + c0 + kb + t] * x8[t];
+        double acc = 0.0;
+        if (tid < kb) {                                   // earlier entries j < kb: z_j -= sum_c L(kb+c, j) x_c
+          const int base = cbm[c0 + tid] + c0 + kb;
+          B2_UNROLL
+          for (int c = 0; c < 8; c++)
+            if (c < pw) acc += Pk[base + c] * x8[c];
+        }
+        __syncthreads();
+        if (tid < kb) xs[c0 + tid] -= acc;
+        if (tid == 0) {
+          B2_UNROLL
+          for (int c = 0; c < 8; c++)
+            if (c < pw) xs[c0 + kb + c] = x8[c];
+        }
+        __syncthreads();
+      }
+    }
   }
   const double sign = (flags & BF_NEGATE) ? -1.0 : 1.0;
   double* dv = dout + (size_t)b * N;
