@@ -341,7 +341,7 @@ def run_b200(args):
 
     batched = None
     if not args.no_batched:
-        batched = bench_batched(args, rank, world, local, dist)
+        batched = bench_batched(args, rank, world, local, dist, fp64_peak=fp64_peak, hbm_peak=hbm_peak)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -372,7 +372,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def bench_batched(args, rank, world, local, dist, total=None, steps=None):
+def bench_batched(args, rank, world, local, dist, total=None, steps=None, fp64_peak=None, hbm_peak=None):
     """C5: `total` independent instances partitioned over the ranks; a step = fused
     factorize + inertia + solve of every instance of the rank (values resident in HBM).
     Returns the "batched" sub-object of the bench line (rank 0) or None."""
@@ -468,10 +468,14 @@ def bench_batched(args, rank, world, local, dist, total=None, steps=None):
            "steps": steps, "n_gpus": world, "scaling": "strong",
            "inertia_ok_at_rho0": int((allrec[:, 0] == 1).sum()), "records_gathered": int(allrec.shape[0]),
            "note_inertia": "instances whose exact-Hessian KKT matrix has the wrong inertia at rho = 0 are the ones newton_system! retries with rho > 0; they are factorized and counted but not solved in this step",
-           "roofline": {"bound": "tensor", "unit": "TFLOP/s",
+           "roofline": {"bound": "tensor", "unit": "TFLOP/s", "kernel": "k_batched<256> (one launch = the rank's instances)",
                         "achieved": flops_inst * (total / world) * steps / (dev_ms * 1e-3) / 1e12,
-                        "note": "per GPU; algorithmic flops sum_j(c_j^2+3c_j) per instance",
-                        "hbm_GBs": (8.0 * nnz + 16.0 * N) * (total / world) * steps / (dev_ms * 1e-3) / 1e9},
+                        "peak": fp64_peak,
+                        "frac": (flops_inst * (total / world) * steps / (dev_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+                        "note": "per GPU; algorithmic flops sum_j(c_j^2+3c_j) per instance; peak = cuBLAS DGEMM measured in this run",
+                        "hbm_view": {"achieved": (8.0 * nnz + 16.0 * N) * (total / world) * steps / (dev_ms * 1e-3) / 1e9,
+                                     "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": ((8.0 * nnz + 16.0 * N) * (total / world) * steps / (dev_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None}},
            "generate_s": t_gen}
     return out
 

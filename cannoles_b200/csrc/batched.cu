@@ -20,6 +20,7 @@ struct BatchEngine {
   int64_t batch = 0;
   cudaStream_t stream = nullptr;
   BatchPlanDev plan{};
+  std::vector<int32_t> cbm_host;
   int smem = 0;
   std::vector<void*> dev_ptrs;
   double* d_vals = nullptr;
@@ -72,16 +73,24 @@ int BatchEngine::init(int dev, int64_t nbatch) {
   B2_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto& e : ev) B2_CUDA_OK(cudaEventCreate(&e));
   for (auto& e : tev) B2_CUDA_OK(cudaEventCreate(&e));
-  const int64_t npacked = (int64_t)N * (N + 1) / 2;
-  smem = (int)batched_smem_bytes(N);
+  // packed lower triangle, column k holding rows k..N-1 at Pk[cbm[k] + row].  Column starts are
+  // padded so that (cbm[k] + k) = 4 (k mod 4) (mod 16): the four columns a DMMA fragment touches
+  // then fall into disjoint shared-memory bank groups (8 consecutive rows x 4 columns, 8-byte words)
+  std::vector<int32_t> cbm(N);
+  int64_t npacked = 0;
+  for (int k = 0; k < N; k++) {
+    while ((npacked & 15) != 4 * (k & 3)) npacked++;
+    cbm[k] = (int32_t)(npacked - k);
+    npacked += N - k;
+  }
+  cbm_host = cbm;
+  smem = (int)batched_smem_bytes(N, npacked);
   if (smem > 227 * 1024 - 64) {
     snprintf(g_last_error, sizeof(g_last_error),
              "b2b_analyze: N = %d needs %d bytes of shared memory per instance (> 227 KB); use the "
              "single-system engine (b2_analyze) for systems this large", N, smem);
     return -1;
   }
-  std::vector<int32_t> cbm(N);
-  for (int k = 0; k < N; k++) cbm[k] = (int32_t)((int64_t)k * N - (int64_t)k * (k - 1) / 2 - k);
   // rows below each supernode
   std::vector<int32_t> rb_ptr(S.nsuper + 1, 0), rb_idx;
   for (int s = 0; s < S.nsuper; s++) {
@@ -428,7 +437,7 @@ int b2b_get_d(b2b_handle* h, int64_t b, double* d) {
   cudaStreamSynchronize(E.stream);
   if (cudaMemcpy(Lh.data(), E.d_L + (size_t)b * E.plan.npacked, Lh.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
     return failb("b2b_get_d: copy failed");
-  for (int k = 0; k < N; k++) d[k] = Lh[(size_t)k * N - (size_t)k * (k - 1) / 2];
+  for (int k = 0; k < N; k++) d[k] = Lh[(size_t)E.cbm_host[k] + k];
   return 0;
 }
 

@@ -41,8 +41,8 @@ struct BatchPlanDev {
 };
 
 // shared memory of k_batched, in bytes, for a system of order N
-inline size_t batched_smem_bytes(int N) {
-  return ((size_t)N * (N + 1) / 2 + 11 * (size_t)N) * sizeof(double) + 3 * (size_t)N * sizeof(int32_t);
+inline size_t batched_smem_bytes(int N, int64_t npacked) {
+  return ((size_t)npacked + 11 * (size_t)N) * sizeof(double) + 3 * (size_t)N * sizeof(int32_t);
 }
 
 // flags: bit0 = write the packed factor to Lout, bit1 = solve with rhs -> dout (only if the
@@ -75,6 +75,7 @@ __device__ __forceinline__ void panel_update(double* Pk, const int32_t* cbm, con
         const int tr = jbeg + (ti0 + a) * 8 + g;        // A-fragment row (local)
         ra[a] = (ti0 + a < nti && tr < m) ? rowmap[tr] : -1;
       }
+#pragma unroll 2
       for (int q0 = 0; q0 < K; q0 += 4) {
         const int q = q0 + t4;
         double bv = 0.0, av[4] = {0.0, 0.0, 0.0, 0.0};
@@ -229,13 +230,21 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
           dd[q] = Pk[cbm[k] + k];
         }
         __syncthreads();
+#ifdef B2_TIMING
+        long long tq = clock64();
+        if (tid == 0 && blockIdx.x == 0) { b2_dbg[50] = 0; b2_dbg[51] = 0; b2_dbg[52] = 0; b2_dbg[53] = 0; }
+#endif
         // (a) left-looking update of the panel with its contributing columns
         if (nct > 0)
           panel_update<NW, false>(Pk, cbm, rowmap, abase, dd, Wd, c0, 0, w, m, nct, warp, lane);
         __syncthreads();
+        B2_ACC(50, tq);
         // (b) dense factorization of the panel, 8 columns at a time
         for (int kb = 0; kb < w; kb += 8) {
           const int pw = min(8, w - kb);
+#ifdef B2_TIMING
+          tq = clock64();
+#endif
           double g[8][8], rd[8], wv[8];
           B2_UNROLL
           for (int c = 0; c < 8; c++)
@@ -249,6 +258,10 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
           for (int c = 0; c < 8; c++)
             wv[c] = (has && c < pw && (tr >= w || kb + c <= tr)) ? Pk[cbm[c0 + kb + c] + gr] : 0.0;
           __syncthreads();                               // the unfactored block has been read by everyone
+          B2_ACC(51, tq);
+#ifdef B2_TIMING
+          tq = clock64();
+#endif
           if (tid < 8) abase[tid] = tid < pw ? cbm[c0 + kb + tid] : 0;
           ldlt8_regs(g, rd);
           B2_UNROLL
@@ -267,9 +280,14 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
             }
           }
           __syncthreads();
+          B2_ACC(52, tq);
+#ifdef B2_TIMING
+          tq = clock64();
+#endif
           if (kb + 8 < w)
             panel_update<NW, true>(Pk, cbm, rowmap, abase, dd, Wd, c0, kb + 8, w, m, pw, warp, lane);
           __syncthreads();
+          B2_ACC(53, tq);
         }
       }
       B2_TICK(33 + 2 * ph);

@@ -30,7 +30,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
   c0 += s0;
   c1 += s1;
 #else
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 #endif

@@ -20,4 +20,5 @@ t = list(out)
 print("assemble", t[31]-t[30])
 print("ph0 (a)", t[32]-t[31], "(b)", t[33]-t[32])
 print("ph1 (a)", t[34]-t[33], "(b)", t[35]-t[34])
+print("root: (a) update", t[50], " panel load", t[51], " ldlt+subst", t[52], " trailing", t[53])
 print("inertia", t[41]-t[40], "solve", t[42]-t[41], "total", t[42]-t[30])
