@@ -51,7 +51,9 @@ int Engine::build_plan() {
   n_small = n_large = 0;
   auto front_m = [&](int s) { return (int)(S.rptr[s + 1] - S.rptr[s]); };
   auto front_w = [&](int s) { return (int)(S.scol[s + 1] - S.scol[s]); };
+  std::vector<size_t> fstart, sstart, bstart;   // first launch of every level in the three lists
   for (int l = 0; l < S.nlevels; l++) {
+    fstart.push_back(fact_launches.size()); sstart.push_back(fwd_launches.size()); bstart.push_back(bwd_launches.size());
     std::vector<int32_t> small[4], large, sol[4], big, tiny[2], tsol[2];
     int small_mmax[4] = {0, 0, 0, 0}, sol_mmax[4] = {0, 0, 0, 0};
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; q++) {
@@ -251,6 +253,22 @@ int Engine::build_plan() {
       if (U.count) fact_launches.push_back(U);
     }
   }
+  // tag every launch with its level and its branch (kernel family): the branches of a level are
+  // independent of each other and are captured as parallel branches of the CUDA graph
+  fstart.push_back(fact_launches.size()); sstart.push_back(fwd_launches.size()); bstart.push_back(bwd_launches.size());
+  auto branch_of = [](const Launch& L) {
+    switch (L.kind) {
+      case LK_FRONT_TINY: case LK_FWD_TINY: case LK_BWD_TINY: return L.cls;          // 0..3
+      case LK_FRONT_SMALL: case LK_FWD: case LK_BWD: return 4 + L.cls;               // 4..7
+      case LK_FWD_BIG: case LK_BWD_BIG: return 8;
+      default: return 9;                                                              // the tiled path: one ordered chain
+    }
+  };
+  for (int l = 0; l < S.nlevels; l++) {
+    for (size_t i = fstart[l]; i < fstart[l + 1]; i++) { fact_launches[i].level = l; fact_launches[i].branch = branch_of(fact_launches[i]); }
+    for (size_t i = sstart[l]; i < sstart[l + 1]; i++) { fwd_launches[i].level = l; fwd_launches[i].branch = branch_of(fwd_launches[i]); }
+    for (size_t i = bstart[l]; i < bstart[l + 1]; i++) { bwd_launches[i].level = l; bwd_launches[i].branch = branch_of(bwd_launches[i]); }
+  }
   // staging area of the factored diagonal blocks + the write-back launch that ends a factorization
   {
     std::vector<int64_t> dsptr(S.nsuper + 1, 0);
@@ -264,6 +282,7 @@ int Engine::build_plan() {
       off += (int64_t)nblk * NB * NB;
     }
     dsptr[S.nsuper] = off;
+    W.level = S.nlevels; W.branch = 9;
     if (W.count) fact_launches.push_back(W);
     if (upload(&d_dsptr, dsptr, bytes_device)) return -1;
     if (dalloc(&d_dstage, (size_t)off, bytes_device)) return -1;
@@ -291,6 +310,9 @@ int Engine::init(int dev) {
   B2_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto& e : ev) B2_CUDA_OK(cudaEventCreate(&e));
   for (auto& e : tev) B2_CUDA_OK(cudaEventCreate(&e));
+  for (auto& s : bstream) B2_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  B2_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  for (auto& e : ev_join) B2_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const Symbolic& S = sym;
   if ((size_t)(S.max_front + SNB) * sizeof(double) > 200 * 1024) {
     snprintf(g_last_error, sizeof(g_last_error), "front of order %d exceeds the solve kernels' shared memory", S.max_front);
@@ -367,82 +389,107 @@ void Engine::destroy() {
   if (h_scalars) cudaFreeHost(h_scalars);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   for (auto& e : tev) if (e) cudaEventDestroy(e);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  for (auto& e : ev_join) if (e) cudaEventDestroy(e);
+  for (auto& s : bstream) if (s) cudaStreamDestroy(s);
   if (stream) cudaStreamDestroy(stream);
 }
 
-int Engine::launch_one(const Launch& L, int pass) {
+int Engine::launch_one(const Launch& L, cudaStream_t st) {
   const int32_t* it = d_items + L.off;
   switch (L.kind) {
     case LK_FRONT_SMALL:
-      if (L.cls == 0) { auto kfn = k_front_small<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, stream, plan, it, L.count, L.smem); }
-      else if (L.cls == 1) { auto kfn = k_front_small<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, stream, plan, it, L.count, 0); }
-      else if (L.cls == 2) { auto kfn = k_front_small<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, stream, plan, it, L.count, 0); }
-      else { auto kfn = k_front_small<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, stream, plan, it, L.count, 0); }
+      if (L.cls == 0) { auto kfn = k_front_small<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, st, plan, it, L.count, L.smem); }
+      else if (L.cls == 1) { auto kfn = k_front_small<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, st, plan, it, L.count, 0); }
+      else if (L.cls == 2) { auto kfn = k_front_small<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, st, plan, it, L.count, 0); }
+      else { auto kfn = k_front_small<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, st, plan, it, L.count, 0); }
       break;
     case LK_ASSEMBLE_LARGE:
-      B2_LAUNCH(k_assemble_large, L.count, 256, 0, stream, plan, it, L.count);
+      B2_LAUNCH(k_assemble_large, L.count, 256, 0, st, plan, it, L.count);
       break;
     case LK_TRSM:
-      B2_LAUNCH(k_trsm, L.count, TRSM_THREADS, TRSM_SMEM, stream, plan, it, L.count, L.jb);
+      B2_LAUNCH(k_trsm, L.count, TRSM_THREADS, TRSM_SMEM, st, plan, it, L.count, L.jb);
       break;
     case LK_DIAG_WRITEBACK:
-      B2_LAUNCH(k_diag_writeback, L.count, 256, 0, stream, plan, it, L.count);
+      B2_LAUNCH(k_diag_writeback, L.count, 256, 0, st, plan, it, L.count);
       break;
     case LK_UPDATE:
-      B2_LAUNCH(k_update, L.count, 256, 0, stream, plan, it, L.count, L.jb, NB, L.mode);
+      B2_LAUNCH(k_update, L.count, 256, 0, st, plan, it, L.count, L.jb, NB, L.mode);
       break;
     case LK_FWD:
-      if (L.cls == 0) { auto kfn = k_fwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, stream, plan, it, L.count, d_x, d_upd, L.smem); }
-      else if (L.cls == 1) { auto kfn = k_fwd<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, stream, plan, it, L.count, d_x, d_upd, 0); }
-      else if (L.cls == 2) { auto kfn = k_fwd<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, stream, plan, it, L.count, d_x, d_upd, 0); }
-      else { auto kfn = k_fwd<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, stream, plan, it, L.count, d_x, d_upd, 0); }
+      if (L.cls == 0) { auto kfn = k_fwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, st, plan, it, L.count, d_x, d_upd, L.smem); }
+      else if (L.cls == 1) { auto kfn = k_fwd<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, st, plan, it, L.count, d_x, d_upd, 0); }
+      else if (L.cls == 2) { auto kfn = k_fwd<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, st, plan, it, L.count, d_x, d_upd, 0); }
+      else { auto kfn = k_fwd<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, st, plan, it, L.count, d_x, d_upd, 0); }
       break;
     case LK_BWD:
-      if (L.cls == 0) { auto kfn = k_bwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, stream, plan, it, L.count, d_x, L.smem); }
-      else if (L.cls == 1) { auto kfn = k_bwd<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, stream, plan, it, L.count, d_x, 0); }
-      else if (L.cls == 2) { auto kfn = k_bwd<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, stream, plan, it, L.count, d_x, 0); }
-      else { auto kfn = k_bwd<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, stream, plan, it, L.count, d_x, 0); }
+      if (L.cls == 0) { auto kfn = k_bwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, st, plan, it, L.count, d_x, L.smem); }
+      else if (L.cls == 1) { auto kfn = k_bwd<64, 1>; B2_LAUNCH(kfn, L.count, 64, L.smem, st, plan, it, L.count, d_x, 0); }
+      else if (L.cls == 2) { auto kfn = k_bwd<128, 1>; B2_LAUNCH(kfn, L.count, 128, L.smem, st, plan, it, L.count, d_x, 0); }
+      else { auto kfn = k_bwd<256, 1>; B2_LAUNCH(kfn, L.count, 256, L.smem, st, plan, it, L.count, d_x, 0); }
       break;
     case LK_FRONT_TINY:
-      if (L.cls == 0) B2_LAUNCH(k_front_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, stream, plan, it, L.count);
-      else B2_LAUNCH(k_front_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count);
+      if (L.cls == 0) B2_LAUNCH(k_front_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, st, plan, it, L.count);
+      else B2_LAUNCH(k_front_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, st, plan, it, L.count);
       break;
     case LK_FWD_TINY:
-      if (L.cls == 0) B2_LAUNCH(k_fwd_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, stream, plan, it, L.count, d_x, d_upd);
-      else if (L.cls == 1) B2_LAUNCH(k_fwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count, d_x, d_upd);
-      else if (L.cls == 2) B2_LAUNCH(k_fwd_tiny<16>, (L.count + tiny_nt(16) - 1) / tiny_nt(16), tiny_nt(16), 0, stream, plan, it, L.count, d_x, d_upd);
-      else B2_LAUNCH(k_fwd_tiny<32>, (L.count + tiny_nt(32) - 1) / tiny_nt(32), tiny_nt(32), 0, stream, plan, it, L.count, d_x, d_upd);
+      if (L.cls == 0) B2_LAUNCH(k_fwd_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, st, plan, it, L.count, d_x, d_upd);
+      else if (L.cls == 1) B2_LAUNCH(k_fwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, st, plan, it, L.count, d_x, d_upd);
+      else if (L.cls == 2) B2_LAUNCH(k_fwd_tiny<16>, (L.count + tiny_nt(16) - 1) / tiny_nt(16), tiny_nt(16), 0, st, plan, it, L.count, d_x, d_upd);
+      else B2_LAUNCH(k_fwd_tiny<32>, (L.count + tiny_nt(32) - 1) / tiny_nt(32), tiny_nt(32), 0, st, plan, it, L.count, d_x, d_upd);
       break;
     case LK_BWD_TINY:
-      if (L.cls == 0) B2_LAUNCH(k_bwd_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, stream, plan, it, L.count, d_x);
-      else if (L.cls == 1) B2_LAUNCH(k_bwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, stream, plan, it, L.count, d_x);
-      else if (L.cls == 2) B2_LAUNCH(k_bwd_tiny<16>, (L.count + tiny_nt(16) - 1) / tiny_nt(16), tiny_nt(16), 0, stream, plan, it, L.count, d_x);
-      else B2_LAUNCH(k_bwd_tiny<32>, (L.count + tiny_nt(32) - 1) / tiny_nt(32), tiny_nt(32), 0, stream, plan, it, L.count, d_x);
+      if (L.cls == 0) B2_LAUNCH(k_bwd_tiny<4>, (L.count + tiny_nt(4) - 1) / tiny_nt(4), tiny_nt(4), 0, st, plan, it, L.count, d_x);
+      else if (L.cls == 1) B2_LAUNCH(k_bwd_tiny<8>, (L.count + tiny_nt(8) - 1) / tiny_nt(8), tiny_nt(8), 0, st, plan, it, L.count, d_x);
+      else if (L.cls == 2) B2_LAUNCH(k_bwd_tiny<16>, (L.count + tiny_nt(16) - 1) / tiny_nt(16), tiny_nt(16), 0, st, plan, it, L.count, d_x);
+      else B2_LAUNCH(k_bwd_tiny<32>, (L.count + tiny_nt(32) - 1) / tiny_nt(32), tiny_nt(32), 0, st, plan, it, L.count, d_x);
       break;
     case LK_FWD_BIG:
-      B2_LAUNCH(k_fwd_big, L.count, 256, 0, stream, plan, it, L.count, d_x, d_upd, d_ypub, d_sflags);
+      B2_LAUNCH(k_fwd_big, L.count, 256, 0, st, plan, it, L.count, d_x, d_upd, d_ypub, d_sflags);
       break;
     case LK_BWD_BIG:
-      B2_LAUNCH(k_bwd_big, L.count, 256, L.smem, stream, plan, it, L.count, d_x, d_sflags + nsflag);
+      B2_LAUNCH(k_bwd_big, L.count, 256, L.smem, st, plan, it, L.count, d_x, d_sflags + nsflag);
       break;
     default: break;
   }
-  (void)pass;
   return 0;
 }
 
-int Engine::run_factor_launches() {
-  for (const Launch& L : fact_launches) launch_one(L, 0);
+// Launch a list level by level.  Inside a level the launches of different branches (kernel
+// families) are independent: they go to side streams forked from / joined back into the main
+// stream, so that under graph capture they become parallel branches of the CUDA graph.
+int Engine::run_list(const std::vector<Launch>& LL) {
+  size_t i = 0;
+  while (i < LL.size()) {
+    size_t j = i;
+    unsigned mask = 0;
+    while (j < LL.size() && LL[j].level == LL[i].level) { mask |= 1u << LL[j].branch; j++; }
+    const bool fork = use_branches && (mask & (mask - 1)) != 0;
+    if (!fork) {
+      for (size_t q = i; q < j; q++) launch_one(LL[q], stream);
+    } else {
+      B2_CUDA_OK(cudaEventRecord(ev_fork, stream));
+      for (int b = 0; b < NBRANCH; b++)
+        if (mask & (1u << b)) B2_CUDA_OK(cudaStreamWaitEvent(bstream[b], ev_fork, 0));
+      for (size_t q = i; q < j; q++) launch_one(LL[q], bstream[LL[q].branch]);
+      for (int b = 0; b < NBRANCH; b++)
+        if (mask & (1u << b)) {
+          B2_CUDA_OK(cudaEventRecord(ev_join[b], bstream[b]));
+          B2_CUDA_OK(cudaStreamWaitEvent(stream, ev_join[b], 0));
+        }
+    }
+    i = j;
+  }
   B2_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+int Engine::run_factor_launches() { return run_list(fact_launches); }
 
 int Engine::run_solve_launches() {
   if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_sflags, 0, (size_t)(2 * nsflag) * sizeof(int), stream));
-  for (const Launch& L : fwd_launches) launch_one(L, 0);
-  for (const Launch& L : bwd_launches) launch_one(L, 1);
-  B2_CUDA_OK(cudaGetLastError());
-  return 0;
+  if (run_list(fwd_launches)) return -1;
+  return run_list(bwd_launches);
 }
 
 #ifdef B2_TIMING
@@ -467,7 +514,7 @@ int Engine::profile(int which, int max, int* kinds, int* cls, int* counts, doubl
     else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_sflags, 0, (size_t)(2 * nsflag) * sizeof(int), stream));
     B2_CUDA_OK(cudaEventRecord(evs[0], stream));
     for (size_t i = 0; i < LL.size(); i++) {
-      launch_one(*LL[i], 0);
+      launch_one(*LL[i], stream);
       B2_CUDA_OK(cudaEventRecord(evs[i + 1], stream));
     }
     B2_CUDA_OK(cudaStreamSynchronize(stream));

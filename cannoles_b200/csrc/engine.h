@@ -32,12 +32,18 @@ struct Launch {
   int jb = 0;         // pivot block origin (tiled path)
   int mode = 0;       // k_update mode
   int smem = 0;       // dynamic shared memory (bytes)
+  int level = 0;      // assembly-tree level (launches of one level are independent across branches)
+  int branch = 0;     // kernel family: launches of one (level, branch) are ordered, branches run concurrently
 };
 
 struct Engine {
   Symbolic sym;
   int device = 0;
   cudaStream_t stream = nullptr;
+  static constexpr int NBRANCH = 10;
+  cudaStream_t bstream[NBRANCH] = {};   // side streams: the branches of one tree level run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[NBRANCH] = {};
+  bool use_branches = true;
   double small_max_m = 72;   // fronts up to this order take the shared-memory path (measured: 72 beats 128 and 40 on C4)
   int tiny_max_m = 8;        // fronts up to this order (4 / 8 classes) take the one-thread-per-front kernels
   int tiny_solve_max_m = 16; // ... and up to this order (16 / 32 classes) in the solves only (measured: 32 loses to a warp per front)
@@ -91,7 +97,8 @@ struct Engine {
   int build_plan();
   int run_factor_launches();
   int run_solve_launches();
-  int launch_one(const Launch& L, int pass);
+  int launch_one(const Launch& L, cudaStream_t st);
+  int run_list(const std::vector<Launch>& LL);
   int profile(int which, int max, int* kinds, int* cls, int* counts, double* ms, int* n);
   int assemble_and_factor(double eig_tol, int64_t* npos, int64_t* nzero, int64_t* nneg, int* breakdown,
                           bool do_assemble);
