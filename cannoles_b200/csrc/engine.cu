@@ -458,38 +458,51 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
 // Launch a list level by level.  Inside a level the launches of different branches (kernel
 // families) are independent: they go to side streams forked from / joined back into the main
 // stream, so that under graph capture they become parallel branches of the CUDA graph.
-int Engine::run_list(const std::vector<Launch>& LL) {
+int Engine::run_list(const std::vector<Launch>& LL, bool allow_fork) {
   size_t i = 0;
   while (i < LL.size()) {
     size_t j = i;
     unsigned mask = 0;
     while (j < LL.size() && LL[j].level == LL[i].level) { mask |= 1u << LL[j].branch; j++; }
-    const bool fork = use_branches && (mask & (mask - 1)) != 0;
+    // A level that contains a flag-chained multi-CTA solve (branch 8) is launched in order on the
+    // main stream: its CTAs form a serial chain, co-resident kernels slow exactly the critical
+    // path and the fork/join edges add latency to it (measured: +6..10 % on the C4 solve).
+    const unsigned excl = mask & (1u << 8);
+    mask &= ~(1u << 8);
+    const bool fork = use_branches && allow_fork && !excl && (mask & (mask - 1)) != 0;
     if (!fork) {
-      for (size_t q = i; q < j; q++) launch_one(LL[q], stream);
+      for (size_t q = i; q < j; q++)
+        if (LL[q].branch != 8) launch_one(LL[q], stream);
     } else {
       B2_CUDA_OK(cudaEventRecord(ev_fork, stream));
       for (int b = 0; b < NBRANCH; b++)
         if (mask & (1u << b)) B2_CUDA_OK(cudaStreamWaitEvent(bstream[b], ev_fork, 0));
-      for (size_t q = i; q < j; q++) launch_one(LL[q], bstream[LL[q].branch]);
+      for (size_t q = i; q < j; q++)
+        if (LL[q].branch != 8) launch_one(LL[q], bstream[LL[q].branch]);
       for (int b = 0; b < NBRANCH; b++)
         if (mask & (1u << b)) {
           B2_CUDA_OK(cudaEventRecord(ev_join[b], bstream[b]));
           B2_CUDA_OK(cudaStreamWaitEvent(stream, ev_join[b], 0));
         }
     }
+    if (excl)
+      for (size_t q = i; q < j; q++)
+        if (LL[q].branch == 8) launch_one(LL[q], stream);
     i = j;
   }
   B2_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int Engine::run_factor_launches() { return run_list(fact_launches); }
+int Engine::run_factor_launches() { return run_list(fact_launches, true); }
 
 int Engine::run_solve_launches() {
   if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_sflags, 0, (size_t)(2 * nsflag) * sizeof(int), stream));
-  if (run_list(fwd_launches)) return -1;
-  return run_list(bwd_launches);
+  // measured: on systems with big fronts (C4) forking the solve levels costs more than it gains
+  // (3.14 -> 3.49 ms), on systems made of small fronts only (C2) it gains 25 %
+  const bool fork = nsflag == 0;
+  if (run_list(fwd_launches, fork)) return -1;
+  return run_list(bwd_launches, fork);
 }
 
 #ifdef B2_TIMING

@@ -98,7 +98,7 @@ struct Engine {
   int run_factor_launches();
   int run_solve_launches();
   int launch_one(const Launch& L, cudaStream_t st);
-  int run_list(const std::vector<Launch>& LL);
+  int run_list(const std::vector<Launch>& LL, bool allow_fork);
   int profile(int which, int max, int* kinds, int* cls, int* counts, double* ms, int* n);
   int assemble_and_factor(double eig_tol, int64_t* npos, int64_t* nzero, int64_t* nneg, int* breakdown,
                           bool do_assemble);
