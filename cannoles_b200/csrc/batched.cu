@@ -154,7 +154,7 @@ int BatchEngine::init(int dev, int64_t nbatch) {
     return -1;
   B2_CUDA_OK(cudaMemset(d_counts, 0, (size_t)batch * 4 * sizeof(long long)));
   B2_CUDA_OK(cudaMallocHost((void**)&h_counts, (size_t)batch * 4 * sizeof(long long)));
-  B2_CUDA_OK(cudaFuncSetAttribute(k_batched<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_batched<BATCH_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   B2_CUDA_OK(cudaDeviceSynchronize());
   return 0;
 }
@@ -171,7 +171,7 @@ void BatchEngine::destroy() {
 int BatchEngine::launch(const double* dv, const double* rho, const double* delta, const uint8_t* act,
                         double eig_tol, const double* rhs, double* out, int flags) {
   B2_CUDA_OK(cudaEventRecord(ev[0], stream));
-  B2_LAUNCH(k_batched<256>, (unsigned)batch, 256, smem, stream, plan, (int)batch, dv, rho, delta, act,
+  B2_LAUNCH(k_batched<BATCH_NT>, (unsigned)batch, BATCH_NT, smem, stream, plan, (int)batch, dv, rho, delta, act,
             eig_tol, d_counts, d_L, rhs, out, flags);
   B2_CUDA_OK(cudaGetLastError());
   B2_CUDA_OK(cudaEventRecord(ev[1], stream));

@@ -49,6 +49,10 @@ inline size_t batched_smem_bytes(int N, int64_t npacked) {
 // inertia is the expected one), bit2 = negate the solution (solve_ldl!'s sign flip),
 // bit3 = read the factor from Lout instead of factorizing (solve-only call)
 constexpr int BF_STORE = 1, BF_SOLVE = 2, BF_NEGATE = 4, BF_LOAD = 8;
+#ifndef B2_BATCH_NT
+#define B2_BATCH_NT 256
+#endif
+constexpr int BATCH_NT = B2_BATCH_NT;   // threads per instance (one CTA per SM: shared memory holds one system)
 
 // C(t, j) -= sum_{q < K} A(t, q) B(j, q) for local columns j in [jbeg, jend) and local rows t in
 // [j, m) of one supernode panel, in 8 x 8 tiles; each warp takes strips of up to four row tiles.
