@@ -372,19 +372,34 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
 #endif
     const int t0 = kb + 8;
     if (t0 < nb) {
-      // thread <-> (row i = t0 + (tid & 63), column parity): S(i,j) -= sum_c L(i,c) W(j,c), j <= i
-      const int i = t0 + (tid & 63);
-      if (i < nb) {
-        double li[8];
+      // S(i,j) -= sum_c L(i,c) W(j,c), t0 <= j <= i < nb.  Thread <-> (row pair, column phase):
+      // rows t0 + p and nb - 1 - p together have nb - t0 + 1 columns whatever p, so the triangle
+      // is balanced; the NT / 32 phases take every (NT/32)-th column.  W(j,:) is a broadcast read.
+      const int n = nb - t0;
+      const int p = tid & 31, phase = tid >> 5;
+      constexpr int NPH = NT / 32;
+      const int iA = t0 + p, iB = nb - 1 - p;
+      if (p < (n + 1) / 2) {
+        const bool two = iB > iA;
+        double la[8], lb[8];
         B2_UNROLL
-        for (int c = 0; c < 8; c++) li[c] = (c < pw) ? S[i + (kb + c) * ld] : 0.0;
-#pragma unroll 4
-        for (int j = t0 + (tid >> 6); j <= i; j += NT / 64) {
+        for (int c = 0; c < 8; c++) {
+          la[c] = (c < pw) ? S[iA + (kb + c) * ld] : 0.0;
+          lb[c] = (c < pw && two) ? S[iB + (kb + c) * ld] : 0.0;
+        }
+        const int jmax = two ? iB : iA;
+#pragma unroll 2
+        for (int j = t0 + phase; j <= jmax; j += NPH) {
           const double* wj = Wd + j * 8;
-          double acc0 = 0.0, acc1 = 0.0;
+          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
           B2_UNROLL
-          for (int c = 0; c < 8; c += 2) { acc0 += li[c] * wj[c]; acc1 += li[c + 1] * wj[c + 1]; }
-          S[i + j * ld] -= acc0 + acc1;
+          for (int c = 0; c < 8; c += 2) {
+            const double w0 = wj[c], w1 = wj[c + 1];
+            a0 += la[c] * w0; a1 += la[c + 1] * w1;
+            b0 += lb[c] * w0; b1 += lb[c + 1] * w1;
+          }
+          if (j <= iA) S[iA + j * ld] -= a0 + a1;
+          if (two) S[iB + j * ld] -= b0 + b1;
         }
       }
     }
@@ -397,8 +412,7 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
 // panel in shared memory (redundantly: a few us of work instead of one more launch on the
 // critical path; chunk 0 stores the factored block in the staging area -- NOT in the panel, which
 // sibling CTAs may still be reading -- and the pivots in dvec), then forms
-// L21 = A21 L11^{-T} D^{-1} for its TRSM_ROWS rows below the block: two rows per thread (16
-// independent FMA chains hide the FP64 latency), rows staged in shared memory, substitution in
+// L21 = A21 L11^{-T} D^{-1} for its TRSM_ROWS rows below the block: TRSM_RPT rows per thread, rows staged in shared memory, substitution in
 // 8-column blocks (rolled loops, 8 x 8 unrolled bodies).
 // Dynamic shared memory: TRSM_SMEM bytes.
 constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + NB * 8 + NB) * (int)sizeof(double);
@@ -444,66 +458,70 @@ __global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t*
   if (tid < NB) dd[tid] = (tid < nb) ? __drcp_rn(S[tid + tid * DIAG_LD]) : 1.0;   // reciprocal pivots
   __syncthreads();                               // S is dead from here on: R takes its place
   B2_TICK(3);
-  // two rows per thread (tid and tid + TRSM_THREADS of the chunk): 16 independent FMA chains
+  // TRSM_RPT rows per thread (tid, tid + TRSM_THREADS, ... of the chunk), two sets of partial sums
+  // per row: 16 * TRSM_RPT independent FMA chains
   const int ibase = jb + nb + chunk * TRSM_ROWS;
   if (ibase + tid >= m) return;                  // no barrier below
-  const int iA = ibase + tid, iB = ibase + TRSM_THREADS + tid;
-  const bool vB = iB < m;
+  int irow[TRSM_RPT];
+  bool vrow[TRSM_RPT];
+  B2_UNROLL
+  for (int h = 0; h < TRSM_RPT; h++) { irow[h] = ibase + h * TRSM_THREADS + tid; vrow[h] = irow[h] < m; }
   for (int k = 0; k < NB; k++) {
-    R[k * TRSM_ROWS + tid] = (k < nb) ? Lp[iA + (size_t)(jb + k) * m] : 0.0;
-    R[k * TRSM_ROWS + TRSM_THREADS + tid] = (k < nb && vB) ? Lp[iB + (size_t)(jb + k) * m] : 0.0;
+    B2_UNROLL
+    for (int h = 0; h < TRSM_RPT; h++)
+      R[k * TRSM_ROWS + h * TRSM_THREADS + tid] = (k < nb && vrow[h]) ? Lp[irow[h] + (size_t)(jb + k) * m] : 0.0;
   }
   B2_TICK(4);
   for (int kb = 0; kb < nb; kb += 8) {
-    double a8[2][8];
+    double a8[TRSM_RPT][8], b8[TRSM_RPT][8];
     B2_UNROLL
-    for (int kk = 0; kk < 8; kk++) {
-      a8[0][kk] = R[(kb + kk) * TRSM_ROWS + tid];
-      a8[1][kk] = R[(kb + kk) * TRSM_ROWS + TRSM_THREADS + tid];
-    }
-    double b8[2][8];   // second set of partial sums: 32 independent FMA chains per thread
-    B2_UNROLL
-    for (int kk = 0; kk < 8; kk++) { b8[0][kk] = 0.0; b8[1][kk] = 0.0; }
-    for (int tb = 0; tb < kb; tb += 8) {
-      double w8[2][8];
+    for (int kk = 0; kk < 8; kk++)
       B2_UNROLL
-      for (int t = 0; t < 8; t++) {
-        w8[0][t] = R[(tb + t) * TRSM_ROWS + tid];
-        w8[1][t] = R[(tb + t) * TRSM_ROWS + TRSM_THREADS + tid];
+      for (int h = 0; h < TRSM_RPT; h++) {
+        a8[h][kk] = R[(kb + kk) * TRSM_ROWS + h * TRSM_THREADS + tid];
+        b8[h][kk] = 0.0;
       }
+    for (int tb = 0; tb < kb; tb += 8) {
+      double w8[TRSM_RPT][8];
+      B2_UNROLL
+      for (int t = 0; t < 8; t++)
+        B2_UNROLL
+        for (int h = 0; h < TRSM_RPT; h++) w8[h][t] = R[(tb + t) * TRSM_ROWS + h * TRSM_THREADS + tid];
       B2_UNROLL
       for (int kk = 0; kk < 8; kk++) {
         const double* lrow = Lr + (kb + kk) * NB + tb;
         B2_UNROLL
         for (int t = 0; t < 8; t += 2) {
           const double l0 = lrow[t], l1 = lrow[t + 1];
-          a8[0][kk] -= w8[0][t] * l0;
-          a8[1][kk] -= w8[1][t] * l0;
-          b8[0][kk] -= w8[0][t + 1] * l1;
-          b8[1][kk] -= w8[1][t + 1] * l1;
+          B2_UNROLL
+          for (int h = 0; h < TRSM_RPT; h++) {
+            a8[h][kk] -= w8[h][t] * l0;
+            b8[h][kk] -= w8[h][t + 1] * l1;
+          }
         }
       }
     }
     B2_UNROLL
-    for (int kk = 0; kk < 8; kk++) { a8[0][kk] += b8[0][kk]; a8[1][kk] += b8[1][kk]; }
+    for (int kk = 0; kk < 8; kk++)
+      B2_UNROLL
+      for (int h = 0; h < TRSM_RPT; h++) a8[h][kk] += b8[h][kk];
     B2_UNROLL
     for (int kk = 1; kk < 8; kk++) {
       const double* lrow = Lr + (kb + kk) * NB + kb;
       B2_UNROLL
       for (int t = 0; t < kk; t++) {
         const double l = lrow[t];
-        a8[0][kk] -= a8[0][t] * l;
-        a8[1][kk] -= a8[1][t] * l;
+        B2_UNROLL
+        for (int h = 0; h < TRSM_RPT; h++) a8[h][kk] -= a8[h][t] * l;
       }
     }
     B2_UNROLL
     for (int kk = 0; kk < 8; kk++) {
-      R[(kb + kk) * TRSM_ROWS + tid] = a8[0][kk];
-      R[(kb + kk) * TRSM_ROWS + TRSM_THREADS + tid] = a8[1][kk];
-      if (kb + kk < nb) {
-        const double rdk = dd[kb + kk];
-        Lp[iA + (size_t)(jb + kb + kk) * m] = a8[0][kk] * rdk;
-        if (vB) Lp[iB + (size_t)(jb + kb + kk) * m] = a8[1][kk] * rdk;
+      const double rdk = dd[(kb + kk) & (NB - 1)];
+      B2_UNROLL
+      for (int h = 0; h < TRSM_RPT; h++) {
+        R[(kb + kk) * TRSM_ROWS + h * TRSM_THREADS + tid] = a8[h][kk];
+        if (kb + kk < nb && vrow[h]) Lp[irow[h] + (size_t)(jb + kb + kk) * m] = a8[h][kk] * rdk;
       }
     }
   }

@@ -37,7 +37,11 @@ constexpr int TILE = 64;      // update tile (TILE x TILE per CTA)
 constexpr int UPD_KC = 16;    // K-chunk of k_update's shared-memory pipeline
 constexpr int DIAG_LD = 65;   // leading dimension of a diagonal block in shared memory
 constexpr int TRSM_THREADS = 128;
-constexpr int TRSM_ROWS = 256;  // rows of the panel per k_trsm CTA (two per thread)
+#ifndef B2_TRSM_RPT
+#define B2_TRSM_RPT 1
+#endif
+constexpr int TRSM_RPT = B2_TRSM_RPT;                 // rows of the panel per k_trsm thread
+constexpr int TRSM_ROWS = TRSM_THREADS * TRSM_RPT;    // ... and per CTA
 constexpr int ASM_TILE = 2048; // doubles in the destination tile of k_assemble_large (8 x 256 or 16 x 128)
 // threads (= fronts) per CTA of the one-thread-per-front kernels for fronts of order <= mm
 #ifdef __CUDACC__
