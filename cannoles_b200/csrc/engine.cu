@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <cstring>
 
@@ -41,11 +42,16 @@ double wall() {
 
 int Engine::build_plan() {
   const Symbolic& S = sym;
+  if (S.uptr[S.nsuper] >= (int64_t)INT32_MAX) {
+    snprintf(g_last_error, sizeof(g_last_error), "update-vector storage exceeds int32 offsets");
+    return -1;
+  }
   std::vector<int32_t> items;
   std::vector<int64_t> asm_cptr(1, 0);   // (tiled front, column block) -> children touching it
   std::vector<int32_t> asm_ent;
-  std::vector<int64_t> asm_off, sb_off;
-  std::vector<int32_t> sb_ent, sb_flag(S.nsuper, 0);   // big-front solve: child entries, flag offsets
+  std::vector<int64_t> asm_off, sb_ptr(1, 0);
+  std::vector<int32_t> sb_src, sb_flag(S.nsuper, 0);   // big-front solve: CSR gather of the child updates, flag offsets
+  int64_t n_gather_chunks = 0;
   nsflag = 0;
   fact_launches.clear(); fwd_launches.clear(); bwd_launches.clear();
   n_small = n_large = 0;
@@ -125,28 +131,30 @@ int Engine::build_plan() {
         sb_flag[s] = (int32_t)nsflag;
         nsflag += nblk;
         rmax = std::max(rmax, m - w);
-        std::vector<std::vector<int32_t>> bucket(nblk + nbel);
+        // per (chunk, row of the chunk): the child update entries that land there, in child order
+        std::vector<std::vector<int32_t>> bucket((size_t)(nblk + nbel) * SB);
         for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
           int c = S.child_idx[q];
           int wc = front_w(c);
           const int32_t* relc = &S.rel[S.rptr[c] + wc];
           int rc = front_m(c) - wc;
-          auto chunk_of = [&](int row) { return row < w ? row / SB : nblk + (row - w) / SB; };
-          int k = 0;
-          while (k < rc) {
-            int ch = chunk_of(relc[k]), ka = k;
-            while (k < rc && chunk_of(relc[k]) == ch) k++;
-            bucket[ch].push_back(c); bucket[ch].push_back(ka); bucket[ch].push_back(k);
+          for (int k = 0; k < rc; k++) {
+            int row = relc[k];
+            int ch = row < w ? row / SB : nblk + (row - w) / SB;
+            int rr = row < w ? row % SB : (row - w) % SB;
+            bucket[(size_t)ch * SB + rr].push_back((int32_t)(S.uptr[c] + k));
           }
         }
         for (int c = 0; c < nblk + nbel; c++) {
-          int e0 = (int)(sb_ent.size() / 2);
-          for (size_t q = 0; q < bucket[c].size(); q += 3) {
-            int ch = bucket[c][q];
-            sb_ent.push_back(bucket[c][q + 1]); sb_ent.push_back(bucket[c][q + 2]);
-            sb_off.push_back(S.rptr[ch] + front_w(ch)); sb_off.push_back(S.uptr[ch]);
+          for (int rr = 0; rr < SB; rr++) {
+            const auto& bk = bucket[(size_t)c * SB + rr];
+            sb_src.insert(sb_src.end(), bk.begin(), bk.end());
+            sb_ptr.push_back((int64_t)sb_src.size());
           }
-          items.push_back(s); items.push_back(c); items.push_back(e0); items.push_back((int)(sb_ent.size() / 2));
+          sb_ptr.push_back((int64_t)sb_src.size());   // pad to SB + 1 pointers per chunk
+          // (pointer layout per chunk g: sb_ptr[g*(SB+1) + r] .. [+ r + 1]; the leading 0 belongs to chunk 0)
+          items.push_back(s); items.push_back(c); items.push_back((int)n_gather_chunks); items.push_back(0);
+          n_gather_chunks++;
           F.count++;
         }
       }
@@ -291,13 +299,13 @@ int Engine::build_plan() {
   if (upload(&d_asm_cptr, asm_cptr, bytes_device)) return -1;
   if (upload(&d_asm_ent, asm_ent, bytes_device)) return -1;
   if (upload(&d_asm_off, asm_off, bytes_device)) return -1;
-  if (upload(&d_sb_off, sb_off, bytes_device)) return -1;
-  plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent; plan.asm_off = d_asm_off; plan.sb_off = d_sb_off;
-  if (upload(&d_sb_ent, sb_ent, bytes_device)) return -1;
+  plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent; plan.asm_off = d_asm_off;
+  if (upload(&d_sb_ptr, sb_ptr, bytes_device)) return -1;
+  if (upload(&d_sb_src, sb_src, bytes_device)) return -1;
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
   if (dalloc(&d_sflags, (size_t)(2 * nsflag), bytes_device)) return -1;
   if (dalloc(&d_ypub, (size_t)S.N, bytes_device)) return -1;
-  plan.sb_ent = d_sb_ent; plan.sb_flag = d_sb_flag;
+  plan.sb_ptr = d_sb_ptr; plan.sb_src = d_sb_src; plan.sb_flag = d_sb_flag;
   std::reverse(bwd_launches.begin(), bwd_launches.end());
   if (upload(&d_items, items, bytes_device)) return -1;
   return 0;
@@ -383,7 +391,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_off, d_sb_off, d_sb_ent, d_sb_flag, d_sflags, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_sflags, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);

@@ -879,7 +879,7 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 #endif
 }
 
-// item = (front, chunk, first entry, end entry): chunk c < nblk owns pivot rows
+// item = (front, chunk, gather id, -): chunk c < nblk owns pivot rows
 // [64c, min(64c+64, w)); chunk c >= nblk owns the rows [w + 64(c-nblk), ...) below the pivots.
 // entries (sb_ent: first / end child row; sb_off: offsets of the child's rel and update vector) list the child update vectors
 // that land in the chunk, in child order.
@@ -901,15 +901,18 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
   __shared__ double Ld[SB * (SB + 1)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = tid & 63, q = tid >> 6;
-  if (tid < SB) t[tid] = (pivot && tid < nrow) ? x[c0 + i0 + tid] : 0.0;
-  __syncthreads();
-  for (int e = items[4 * b + 2]; e < items[4 * b + 3]; e++) {
-    const int ka = P.sb_ent[2 * e], kz = P.sb_ent[2 * e + 1];
-    const int32_t* relc = P.rel + P.sb_off[2 * e];
-    const double* uc = upd + P.sb_off[2 * e + 1];
-    for (int k = ka + tid; k < kz; k += 256) t[relc[k] - i0] += uc[k];
-    __syncthreads();
+  // t = own entries of the right-hand side + the children's update vectors: a CSR gather built on
+  // the host (row r of the chunk sums upd[sb_src[e]], e in [sb_ptr[g + r], sb_ptr[g + r + 1]), in
+  // child order => deterministic), one thread per row, no barriers, loads independent
+  if (tid < SB) {
+    double acc = (pivot && tid < nrow) ? x[c0 + i0 + tid] : 0.0;
+    const int64_t gb = (int64_t)items[4 * b + 2] * (SB + 1);
+    const int64_t e1 = P.sb_ptr[gb + tid + 1];
+#pragma unroll 4
+    for (int64_t e = P.sb_ptr[gb + tid]; e < e1; e++) acc += upd[P.sb_src[e]];
+    t[tid] = acc;
   }
+  __syncthreads();
   if (pivot) {  // own diagonal block, strict lower part (prefetched before any wait)
     for (int e = tid; e < SB * SB; e += 256) {
       const int i = e % SB, j = e / SB;

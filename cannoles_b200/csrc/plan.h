@@ -26,8 +26,8 @@ struct PlanDev {
   const int64_t* asm_cptr; // per (tiled front, destination column block): range in asm_ent
   const int32_t* asm_ent;  // per entry: first child column, end child column, child rows below, pad
   const int64_t* asm_off;  // per entry: offset of the child's rel[] and of its contribution block
-  const int32_t* sb_ent;   // big-front solve, per entry: first child row, end child row
-  const int64_t* sb_off;   // per entry: offset of the child's rel[] and of its update vector
+  const int64_t* sb_ptr;   // big-front solve: per (chunk, row) CSR pointers into sb_src (SB + 1 per chunk)
+  const int32_t* sb_src;   // offsets into the update-vector storage, in child order
   const int32_t* sb_flag;  // per front: offset of its block flags (big fronts only)
   int* flags;  // [0] = breakdown (exact zero pivot seen)
 };
