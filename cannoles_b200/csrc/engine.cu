@@ -303,8 +303,7 @@ int Engine::build_plan() {
   if (upload(&d_sb_ptr, sb_ptr, bytes_device)) return -1;
   if (upload(&d_sb_src, sb_src, bytes_device)) return -1;
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
-  if (dalloc(&d_sflags, (size_t)(2 * nsflag), bytes_device)) return -1;
-  if (dalloc(&d_ypub, (size_t)S.N, bytes_device)) return -1;
+  if (dalloc(&d_ypub, (size_t)(2 * S.N), bytes_device)) return -1;   // forward | backward publication slots
   plan.sb_ptr = d_sb_ptr; plan.sb_src = d_sb_src; plan.sb_flag = d_sb_flag;
   std::reverse(bwd_launches.begin(), bwd_launches.end());
   if (upload(&d_items, items, bytes_device)) return -1;
@@ -391,7 +390,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_sflags, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);
@@ -453,10 +452,10 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       else B2_LAUNCH(k_bwd_tiny<32>, (L.count + tiny_nt(32) - 1) / tiny_nt(32), tiny_nt(32), 0, st, plan, it, L.count, d_x);
       break;
     case LK_FWD_BIG:
-      B2_LAUNCH(k_fwd_big, L.count, 256, 0, st, plan, it, L.count, d_x, d_upd, d_ypub, d_sflags);
+      B2_LAUNCH(k_fwd_big, L.count, 256, 0, st, plan, it, L.count, d_x, d_upd, d_ypub);
       break;
     case LK_BWD_BIG:
-      B2_LAUNCH(k_bwd_big, L.count, 256, L.smem, st, plan, it, L.count, d_x, d_sflags + nsflag);
+      B2_LAUNCH(k_bwd_big, L.count, 256, L.smem, st, plan, it, L.count, d_x, d_ypub + sym.N);
       break;
     default: break;
   }
@@ -505,7 +504,8 @@ int Engine::run_list(const std::vector<Launch>& LL, bool allow_fork) {
 int Engine::run_factor_launches() { return run_list(fact_launches, true); }
 
 int Engine::run_solve_launches() {
-  if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_sflags, 0, (size_t)(2 * nsflag) * sizeof(int), stream));
+  // publication slots of the multi-CTA solves: all-ones = "not yet published" (poll_value)
+  if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
   // measured: on systems with big fronts (C4) forking the solve levels costs more than it gains
   // (3.14 -> 3.49 ms), on systems made of small fronts only (C2) it gains 25 %
   const bool fork = nsflag == 0;
@@ -532,7 +532,7 @@ int Engine::profile(int which, int max, int* kinds, int* cls, int* counts, doubl
   for (auto& e : evs) B2_CUDA_OK(cudaEventCreate(&e));
   for (int rep = 0; rep < 2; rep++) {   // second pass is the warm one
     if (which == 0) B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
-    else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_sflags, 0, (size_t)(2 * nsflag) * sizeof(int), stream));
+    else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
     B2_CUDA_OK(cudaEventRecord(evs[0], stream));
     for (size_t i = 0; i < LL.size(); i++) {
       launch_one(*LL[i], stream);

@@ -61,9 +61,8 @@ struct Engine {
   double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr, *d_dstage = nullptr;
   int64_t *d_dsptr = nullptr, *d_asm_cptr = nullptr, *d_asm_off = nullptr, *d_sb_ptr = nullptr;
   int32_t *d_asm_ent = nullptr, *d_sb_src = nullptr, *d_sb_flag = nullptr;
-  int* d_sflags = nullptr;     // block flags of the big-front solves: [0, nsflag) forward, [nsflag, 2 nsflag) backward
-  int64_t nsflag = 0;
-  double* d_ypub = nullptr;    // unscaled forward solutions published between the CTAs of a big front
+  int64_t nsflag = 0;          // pivot blocks of the big fronts (0: no multi-CTA solves)
+  double* d_ypub = nullptr;    // 2 N publication slots (forward y | backward x) of the multi-CTA solves
   int* d_flags = nullptr;
   unsigned long long* d_counts = nullptr;
   int32_t* d_items = nullptr;

@@ -858,24 +858,35 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_bwd_tiny(PlanDev P, const int32
 // prefetched into registers BEFORE it waits, so the chain per block is: flag round trip +
 // 64 x 64 mat-vec + in-block substitution by one warp.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void wait_flag(const int* flag) {
+// Publishing between the CTAs of one launch: a slot holds the all-ones NaN pattern (the buffer is
+// memset to 0xFF at the start of a sweep) until its value is stored; a consumer polls the slot
+// itself, so one L2 round trip hands a value over (no separate flag, no fence: an aligned 8-byte
+// store is atomic and nothing else is published with it).
+__device__ __forceinline__ double poll_value(const double* p) {
 #ifdef B2_EMULATE
   // the emulator runs the CTAs one after the other in blockIdx order: the producer must be done
-  if (threadIdx.x == 0 && *flag == 0) { fprintf(stderr, "k_*_big: wait on a CTA that has not run\n"); abort(); }
-#else
-  if (threadIdx.x == 0) {
-    while (*reinterpret_cast<const volatile int*>(flag) == 0) { }
-    __threadfence();
-  }
-#endif
-  __syncthreads();
-}
-
-__device__ __forceinline__ double ld_cg(const double* p) {
-#ifdef B2_EMULATE
+  unsigned long long u;
+  memcpy(&u, p, 8);
+  if (u == ~0ull) { fprintf(stderr, "k_*_big: wait on a CTA that has not run\n"); abort(); }
   return *p;
 #else
-  return __ldcg(p);
+  const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(p);
+  unsigned long long u = *q;
+  while (u == ~0ull) u = *q;
+  return __longlong_as_double((long long)u);
+#endif
+}
+
+__device__ __forceinline__ void publish_value(double* p, double v) {
+#ifdef B2_EMULATE
+  unsigned long long u;
+  memcpy(&u, &v, 8);
+  if (u == ~0ull) u = 0x7ff8000000000000ull;
+  memcpy(p, &u, 8);
+#else
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  if (u == ~0ull) u = 0x7ff8000000000000ull;   // never publish the sentinel itself
+  *reinterpret_cast<volatile unsigned long long*>(p) = u;
 #endif
 }
 
@@ -885,7 +896,7 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 // that land in the chunk, in child order.
 __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __restrict__ items, int nitems,
                                                  double* __restrict__ x, double* __restrict__ upd,
-                                                 double* __restrict__ ypub, int* __restrict__ flags) {
+                                                 double* __restrict__ ypub) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
   const int s = items[4 * b], c = items[4 * b + 1];
@@ -896,7 +907,6 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
   const int i0 = pivot ? c * SB : w + (c - nblk) * SB;
   const int nrow = min(SB, (pivot ? w : m) - i0);
   const double* Lp = P.Lx + P.lptr[s];
-  int* fl = flags + P.sb_flag[s];
   __shared__ double t[SB], yb[SB], red[4][SB];
   __shared__ double Ld[SB * (SB + 1)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -932,8 +942,7 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
   };
   if (nprev > 0) prefetch(0);
   for (int blk = 0; blk < nprev; blk++) {
-    wait_flag(fl + blk);
-    if (tid < SB) yb[tid] = (blk * SB + tid < w) ? ld_cg(ypub + c0 + blk * SB + tid) : 0.0;
+    if (tid < SB) yb[tid] = (blk * SB + tid < w) ? poll_value(ypub + c0 + blk * SB + tid) : 0.0;
     __syncthreads();
     double acc = 0.0, acc2 = 0.0;
     B2_UNROLL
@@ -948,26 +957,45 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
     __syncthreads();
   }
   if (pivot) {
-    // unit-lower substitution inside the block by warp 0: lane holds rows lane and lane + 32
+    // unit-lower substitution inside the block by warp 0, 8 columns at a time: every lane solves
+    // the 8 x 8 triangle redundantly in registers (no communication on the chain), then updates
+    // its two rows (lane, lane + 32) below it
     if (warp == 0) {
       double t0 = t[lane], t1 = t[lane + 32];
-      for (int k = 0; k < nrow; k++) {
-        const double yk = __shfl_sync(0xffffffffu, (k < 32) ? t0 : t1, k & 31);
-        const double* col = Ld + k * (SB + 1);
-        if (lane > k) t0 -= col[lane] * yk;
-        if (lane + 32 > k) t1 -= col[lane + 32] * yk;
+      for (int kb = 0; kb < nrow; kb += 8) {
+        double y8[8];
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) y8[c] = t[kb + c];
+        B2_UNROLL
+        for (int c = 1; c < 8; c++)
+          B2_UNROLL
+          for (int tt = 0; tt < c; tt++) y8[c] -= Ld[(kb + c) + (kb + tt) * (SB + 1)] * y8[tt];
+        double u0 = 0.0, u1 = 0.0;
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) {
+          const double* col = Ld + (kb + c) * (SB + 1);
+          u0 += col[lane] * y8[c];
+          u1 += col[lane + 32] * y8[c];
+        }
+        __syncwarp();
+        // rows inside the 8-block take the solved values, rows below it the update
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) {
+          if (lane == kb + c) t0 = y8[c];
+          if (lane + 32 == kb + c) t1 = y8[c];
+        }
+        if (lane >= kb + 8) t0 -= u0;
+        if (lane + 32 >= kb + 8) t1 -= u1;
+        t[lane] = t0;
+        t[lane + 32] = t1;
+        __syncwarp();
       }
-      t[lane] = t0;
-      t[lane + 32] = t1;
     }
     __syncthreads();
     if (tid < nrow) {
-      ypub[c0 + i0 + tid] = t[tid];
+      publish_value(ypub + c0 + i0 + tid, t[tid]);
       x[c0 + i0 + tid] = t[tid] / P.dvec[c0 + i0 + tid];
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) fl[c] = 1;
   } else {
     if (tid < nrow) upd[P.uptr[s] + (i0 - w) + tid] = t[tid];
   }
@@ -975,7 +1003,7 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
 
 // item = (front, column block), blocks of a front in DESCENDING order.
 __global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __restrict__ items, int nitems,
-                                                 double* __restrict__ x, int* __restrict__ flags) {
+                                                 double* __restrict__ x, double* __restrict__ xpub) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
   const int s = items[2 * b], c = items[2 * b + 1];
@@ -985,12 +1013,12 @@ __global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __res
   const int nblk = (w + SB - 1) / SB;
   const int j0 = c * SB, ncol = min(SB, w - j0);
   const double* Lp = P.Lx + P.lptr[s];
-  int* fl = flags + P.sb_flag[s];
   B2_DYN_SMEM(raw);
   double* xb = reinterpret_cast<double*>(raw);        // x of the rows below the pivots (m - w)
   __shared__ double sc[SB], xd[SB];
   __shared__ double Ld[SB * (SB + 1)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  B2_TICK(54);
   if (tid < SB) sc[tid] = (tid < ncol) ? x[c0 + j0 + tid] : 0.0;
   for (int i = w + tid; i < m; i += 256) xb[i - w] = x[P.rowidx[r0 + i]];
   for (int e = tid; e < SB * SB; e += 256) {   // own diagonal block: Ld[i][j] = L(j0+i, j0+j), j < i
@@ -998,18 +1026,31 @@ __global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __res
     Ld[i + j * (SB + 1)] = (i < ncol && j < i) ? Lp[(j0 + i) + (size_t)(j0 + j) * m] : 0.0;
   }
   __syncthreads();
-  // rows below the pivots: sc[k] -= sum_i L(i, j0+k) xb[i]; one warp per column, lanes over rows
-  for (int k = warp; k < ncol; k += 8) {
-    const double* col = Lp + (size_t)(j0 + k) * m;
-    double acc = 0.0, acc2 = 0.0;
-    int i = w + lane;
-    for (; i + 32 < m; i += 64) { acc += col[i] * xb[i - w]; acc2 += col[i + 32] * xb[i + 32 - w]; }
-    if (i < m) acc += col[i] * xb[i - w];
-    acc += acc2;
+  B2_TICK(55);
+  // rows below the pivots: sc[k] -= sum_i L(i, j0+k) xb[i]; every warp takes the columns
+  // warp, warp + 8, ... together (one pass over the rows, eight independent sums), lanes over rows
+  if (m > w) {
+    double acc[8];
+    const double* colp[8];
     B2_UNROLL
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) sc[k] -= acc;
+    for (int kk = 0; kk < 8; kk++) {
+      acc[kk] = 0.0;
+      colp[kk] = Lp + (size_t)(j0 + min(warp + 8 * kk, ncol - 1)) * m;
+    }
+    for (int i = w + lane; i < m; i += 32) {
+      const double xv = xb[i - w];
+      B2_UNROLL
+      for (int kk = 0; kk < 8; kk++) acc[kk] += colp[kk][i] * xv;
+    }
+    B2_UNROLL
+    for (int kk = 0; kk < 8; kk++) {
+      double v = acc[kk];
+      B2_UNROLL
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && warp + 8 * kk < ncol) sc[warp + 8 * kk] -= v;
+    }
   }
+  B2_TICK(56);
   // later pivot blocks of the same front, as they are published
   double lreg[8][2];
   auto prefetch = [&](int d) {
@@ -1024,8 +1065,7 @@ __global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __res
   };
   if (c + 1 < nblk) prefetch(nblk - 1);
   for (int d = nblk - 1; d > c; d--) {
-    wait_flag(fl + d);
-    if (tid < SB) xd[tid] = (d * SB + tid < w) ? ld_cg(x + c0 + d * SB + tid) : 0.0;
+    if (tid < SB) xd[tid] = (d * SB + tid < w) ? poll_value(xpub + c0 + d * SB + tid) : 0.0;
     __syncthreads();
     double part[8];
     B2_UNROLL
@@ -1041,21 +1081,41 @@ __global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __res
     __syncthreads();
   }
   __syncthreads();
-  // L_cc^T x = sc inside the block by warp 0: lane holds entries lane and lane + 32
+  B2_TICK(57);
+  // L_cc^T x = sc inside the block by warp 0, 8 columns at a time from the end: every lane solves
+  // the 8 x 8 triangle redundantly, then updates its two entries (lane, lane + 32) before it
   if (warp == 0) {
     double s0 = sc[lane], s1 = sc[lane + 32];
-    for (int k = ncol - 1; k >= 0; k--) {
-      const double xk = __shfl_sync(0xffffffffu, (k < 32) ? s0 : s1, k & 31);
-      // entries j < k: s_j -= L(j0+k, j0+j) xk = Ld[k + j*(SB+1)]
-      if (lane < k) s0 -= Ld[k + lane * (SB + 1)] * xk;
-      if (lane + 32 < k) s1 -= Ld[k + (lane + 32) * (SB + 1)] * xk;
+    for (int kb = ((ncol - 1) >> 3) << 3; kb >= 0; kb -= 8) {
+      double x8[8];
+      B2_UNROLL
+      for (int c2 = 0; c2 < 8; c2++) x8[c2] = sc[kb + c2];
+      B2_UNROLL
+      for (int c2 = 6; c2 >= 0; c2--)
+        B2_UNROLL
+        for (int tt = c2 + 1; tt < 8; tt++) x8[c2] -= Ld[(kb + tt) + (kb + c2) * (SB + 1)] * x8[tt];
+      double u0 = 0.0, u1 = 0.0;   // entries j < kb: s_j -= sum_c L(j0+kb+c, j0+j) x_c = Ld[(kb+c) + j*(SB+1)]
+      B2_UNROLL
+      for (int c2 = 0; c2 < 8; c2++) {
+        u0 += Ld[(kb + c2) + lane * (SB + 1)] * x8[c2];
+        u1 += Ld[(kb + c2) + (lane + 32) * (SB + 1)] * x8[c2];
+      }
+      __syncwarp();
+      B2_UNROLL
+      for (int c2 = 0; c2 < 8; c2++) {
+        if (lane == kb + c2) s0 = x8[c2];
+        if (lane + 32 == kb + c2) s1 = x8[c2];
+      }
+      if (lane < kb) s0 -= u0;
+      if (lane + 32 < kb) s1 -= u1;
+      sc[lane] = s0;
+      sc[lane + 32] = s1;
+      __syncwarp();
     }
-    if (lane < ncol) x[c0 + j0 + lane] = s0;
-    if (lane + 32 < ncol) x[c0 + j0 + lane + 32] = s1;
+    if (lane < ncol) { x[c0 + j0 + lane] = s0; publish_value(xpub + c0 + j0 + lane, s0); }
+    if (lane + 32 < ncol) { x[c0 + j0 + lane + 32] = s1; publish_value(xpub + c0 + j0 + lane + 32, s1); }
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) fl[c] = 1;
+  B2_TICK(58);
 }
 
 __global__ void __launch_bounds__(256) k_perm_in(int64_t n, const int32_t* __restrict__ perm,

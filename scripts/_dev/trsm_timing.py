@@ -13,6 +13,10 @@ B = B200Struct(N, r, c, v, nvar=nv, nequ=ne, ncon=nc, ordering=1, shift_retries=
 for _ in range(3):
     ok = B.try_to_factorize(v, nv, ne, nc, EPS)
 print(ok, B.stats()["max_front"], B.timings())
+d = np.zeros(N)
+for _ in range(3):
+    B.solve_ldl(np.ones(N), d)
+print("solve", B.timings(), B.last_relres)
 out = (C.c_longlong * 64)()
 lib.b2_debug_clocks.argtypes = [C.POINTER(C.c_longlong)]
 print("rc", lib.b2_debug_clocks(out))
@@ -22,4 +26,5 @@ print("ldlt total  ", t[2] - t[1], " panels", t[10], " trailing", t[11])
 print("Lr build    ", t[3] - t[2])
 print("R load      ", t[4] - t[3])
 print("substitution", t[5] - t[4])
+print("bwd_big CTA0 (last block of the front): init+gather", t[55]-t[54], " rows below", t[56]-t[55], " later blocks", t[57]-t[56], " substitution", t[58]-t[57], " publish", t[59]-t[58])
 print("update: first load", t[21]-t[20], " main loop", t[22]-t[21], " epilogue", t[23]-t[22])
