@@ -435,6 +435,8 @@ def bench_batched(args, rank, world, local, dist, total=None, steps=None, fp64_p
     dev_ms = ms.value
     # end to end from pinned-size host arrays through the public verb
     d = np.zeros((nb, N))
+    for arr in (vals, rhs, d):
+        Bt.register_host(arr)
     ok = Bt.factor_solve(vals, rhs, d)
     sync()
     t1 = time.perf_counter()
@@ -463,6 +465,33 @@ def bench_batched(args, rank, world, local, dist, total=None, steps=None, fp64_p
     if rank != 0:
         return None
     flops_inst = st["flops"]
+    # CPU baseline for the batch: the oracle port on a bounded sample of the same instances, one
+    # oracle handle per host thread (ctypes releases the GIL), all host cores
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        import threading
+        from oracle import LDLFactStruct
+        ncores = os.cpu_count() or 1
+        nsample = min(nb, 32 * ncores)
+        handles = [LDLFactStruct(N, s.rows, s.cols, vals[0].copy()) for _ in range(ncores)]
+
+        def work(tix):
+            O = handles[tix]
+            dd = np.zeros(N)
+            for bidx in range(tix, nsample, ncores):
+                O.try_to_factorize(vals[bidx], nv, ne, nc, EPS)   # (a wrong inertia at rho = 0 is legitimate)
+                O.solve_ldl(rhs[bidx], dd)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(ncores)]
+        t0c = time.perf_counter()
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        tc = time.perf_counter() - t0c
+        cpu = {"value": nsample / tc, "unit": "instances/s", "cores": ncores, "kind": "port",
+               "sample": f"{nsample} of the {total} instances, factor+solve each (AMD, up-looking LDL^T), "
+                         f"{ncores} host threads"}
     out = {"metric": "batched_kkt_factor_solve_per_s", "unit": "instances/s",
            "value": total * steps / (dev_ms * 1e-3), "ms_per_step": dev_ms / steps,
            "e2e": {"value": total * e2e_steps / (e2e_ms * 1e-3), "unit": "instances/s",
@@ -485,7 +514,7 @@ def bench_batched(args, rank, world, local, dist, total=None, steps=None, fp64_p
                         "hbm_view": {"achieved": (8.0 * nnz + 16.0 * N) * (total / world) * steps / (dev_ms * 1e-3) / 1e9,
                                      "peak": hbm_peak, "unit": "GB/s",
                                      "frac": ((8.0 * nnz + 16.0 * N) * (total / world) * steps / (dev_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None}},
-           "generate_s": t_gen}
+           "cpu_baseline": cpu, "generate_s": t_gen}
     return out
 
 

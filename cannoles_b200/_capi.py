@@ -40,6 +40,7 @@ EXPORTS = [
     "b2b_solve_dev", "b2b_factor_solve", "b2b_factor_solve_dev", "b2b_stats", "b2b_last_ms",
     "b2b_timer_start", "b2b_timer_stop", "b2b_get_perm", "b2b_get_d", "b2b_free",
     "b2_dev_malloc", "b2_dev_free", "b2_dev_upload", "b2_dev_download", "b2_dev_sync",
+    "b2_host_register", "b2_host_unregister",
     "b2_measure_dgemm", "b2_measure_hbm",
 ]
 
@@ -93,6 +94,9 @@ def bind_library(path: str):
         lib.b2_dev_free.argtypes = [vp]
         lib.b2_dev_upload.argtypes = [vp, vp, C.c_size_t]
         lib.b2_dev_download.argtypes = [vp, vp, C.c_size_t]
+    if hasattr(lib, "b2_host_register"):
+        lib.b2_host_register.argtypes = [vp, C.c_size_t]
+        lib.b2_host_unregister.argtypes = [vp]
     if hasattr(lib, "b2_measure_dgemm"):
         lib.b2_measure_dgemm.argtypes = [C.c_int, C.c_int, pd, pd]
         lib.b2_measure_hbm.argtypes = [C.c_size_t, C.c_int, pd]

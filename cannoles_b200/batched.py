@@ -59,12 +59,24 @@ class B200BatchStruct:
         self.nneg = np.zeros(B, dtype=np.int64)
         self.breakdown = np.zeros(B, dtype=np.int32)
         self.nfactorize_calls = 0
+        self._pinned = []
 
     def _check(self, rc):
         if rc != 0:
             raise B200Error(_capi.last_error(self._lib))
 
+    def register_host(self, arr) -> bool:
+        """Pin a caller-owned array (values, right-hand sides, steps) so that the H2D / D2H copies of
+        the batched verbs run at PCIe speed instead of through a pageable staging buffer."""
+        rc = self._lib.b2_host_register(arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+        if rc == 0:
+            self._pinned.append(arr)
+        return rc == 0
+
     def close(self):
+        for a in getattr(self, "_pinned", []):
+            self._lib.b2_host_unregister(a.ctypes.data_as(C.c_void_p))
+        self._pinned = []
         h = getattr(self, "_h", None)
         if h is not None and h.value:
             self._lib.b2b_free(h)

@@ -239,6 +239,18 @@ int b2_dev_download(void* hptr, const void* dptr, size_t bytes) {
   if (cudaMemcpy(hptr, dptr, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return fail("b2_dev_download failed");
   return 0;
 }
+int b2_host_register(void* ptr, size_t bytes) {
+  if (!ptr) return fail("b2_host_register: NULL");
+  if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return fail("b2_host_register: cudaHostRegister failed");
+  }
+  return 0;
+}
+int b2_host_unregister(void* ptr) {
+  if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return fail("b2_host_unregister failed"); }
+  return 0;
+}
 int b2_dev_sync(void) {
   if (cudaDeviceSynchronize() != cudaSuccess) return fail("b2_dev_sync failed");
   return 0;

@@ -173,6 +173,9 @@ int b2_dev_free(void* dptr);
 int b2_dev_upload(void* dptr, const void* hptr, size_t bytes);
 int b2_dev_download(void* hptr, const void* dptr, size_t bytes);
 int b2_dev_sync(void);
+/* pin / unpin a caller-owned host buffer without a handle (batched values, right-hand sides) */
+int b2_host_register(void* ptr, size_t bytes);
+int b2_host_unregister(void* ptr);
 /* FP64 GEMM throughput of this library's own tile kernel and of cuBLAS DGEMM (TFLOP/s), the
  * roofline denominator for the frontal updates (MEASURED_PEAKS.json has no FP64 entry). */
 int b2_measure_dgemm(int n, int reps, double* tflops_own, double* tflops_cublas);
