@@ -47,8 +47,8 @@ int Engine::build_plan() {
     return -1;
   }
   std::vector<int32_t> items;
-  std::vector<int64_t> asm_cptr(1, 0);   // (tiled front, column block) -> children touching it
-  std::vector<int32_t> asm_ent;
+  std::vector<int64_t> asm_cptr(1, 0);   // destination column of a tiled front -> (child, child column) pairs
+  std::vector<int32_t> asm_ent, asm_rc;
   std::vector<int64_t> asm_off, sb_ptr(1, 0);
   std::vector<int32_t> sb_src, sb_flag(S.nsuper, 0);   // big-front solve: CSR gather of the child updates, flag offsets
   int64_t n_gather_chunks = 0;
@@ -174,30 +174,24 @@ int Engine::build_plan() {
         int m = front_m(s);
         const int acols = m <= 128 ? 16 : 8, arows = ASM_TILE / acols;   // tile shape of this front
         int ncb = (m + acols - 1) / acols, nrb = (m + arows - 1) / arows;
-        // children (ascending, the extend-add order) bucketed by the column blocks they touch
-        const int gbase = (int)asm_cptr.size() - 1;
-        std::vector<std::vector<int32_t>> bucket(ncb);
+        // per destination column: the (child descriptor, child column) pairs that land on it, children
+        // ascending (the extend-add order)
+        const int64_t gbase = (int64_t)asm_cptr.size() - 1;   // global id of this front's column 0
+        std::vector<std::vector<int32_t>> percol(m);
         for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
           int c = S.child_idx[q];
           int wc = front_w(c);
           const int32_t* relc = &S.rel[S.rptr[c] + wc];
           int rc = front_m(c) - wc;
-          int j = 0;
-          while (j < rc) {
-            int blk = relc[j] / acols, ja = j;
-            while (j < rc && relc[j] / acols == blk) j++;
-            bucket[blk].push_back(c); bucket[blk].push_back(ja); bucket[blk].push_back(j);
-          }
+          if (rc == 0) continue;
+          const int32_t ce = (int32_t)asm_rc.size();
+          asm_rc.push_back(rc);
+          asm_off.push_back(S.rptr[c] + wc); asm_off.push_back(S.cbptr[c]);
+          for (int j = 0; j < rc; j++) { percol[relc[j]].push_back(ce); percol[relc[j]].push_back(j); }
         }
-        for (int cb = 0; cb < ncb; cb++) {
-          for (size_t q = 0; q < bucket[cb].size(); q += 3) {
-            int ch = bucket[cb][q];
-            int wch = front_w(ch);
-            asm_ent.push_back(bucket[cb][q + 1]); asm_ent.push_back(bucket[cb][q + 2]);
-            asm_ent.push_back(front_m(ch) - wch); asm_ent.push_back(0);
-            asm_off.push_back(S.rptr[ch] + wch); asm_off.push_back(S.cbptr[ch]);
-          }
-          asm_cptr.push_back((int64_t)asm_ent.size() / 4);
+        for (int J = 0; J < m; J++) {
+          asm_ent.insert(asm_ent.end(), percol[J].begin(), percol[J].end());
+          asm_cptr.push_back((int64_t)asm_ent.size() / 2);
         }
         const int32_t* apos = S.amap_pos.data() + S.amap_ptr[s];
         const int64_t na = S.amap_ptr[s + 1] - S.amap_ptr[s];
@@ -212,7 +206,7 @@ int Engine::build_plan() {
           }
           for (int rb = 0; rb < nrb; rb++) {
             if ((rb + 1) * arows <= cb * acols) continue;   // tile entirely above the diagonal
-            items.push_back(s); items.push_back(j0); items.push_back(rb * arows); items.push_back(gbase + cb);
+            items.push_back(s); items.push_back(j0); items.push_back(rb * arows); items.push_back((int32_t)(gbase + j0));
             items.push_back(qa); items.push_back(qb); items.push_back(acols); items.push_back(arows);
             L.count++;
           }
@@ -298,8 +292,10 @@ int Engine::build_plan() {
   }
   if (upload(&d_asm_cptr, asm_cptr, bytes_device)) return -1;
   if (upload(&d_asm_ent, asm_ent, bytes_device)) return -1;
+  if (upload(&d_asm_rc, asm_rc, bytes_device)) return -1;
+  if ((int64_t)asm_cptr.size() >= (int64_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "too many tiled-front columns"); return -1; }
   if (upload(&d_asm_off, asm_off, bytes_device)) return -1;
-  plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent; plan.asm_off = d_asm_off;
+  plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent; plan.asm_rc = d_asm_rc; plan.asm_off = d_asm_off;
   if (upload(&d_sb_ptr, sb_ptr, bytes_device)) return -1;
   if (upload(&d_sb_src, sb_src, bytes_device)) return -1;
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
@@ -390,7 +386,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);

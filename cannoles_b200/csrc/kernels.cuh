@@ -221,17 +221,16 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_front_tiny(PlanDev P, const int
 // pass with K = w forms the contribution block.
 // ------------------------------------------------------------------------------------------
 
-// item = (front, first destination column, first destination row, global column-block id,
+// item = (front, first destination column, first destination row, global id of that column,
 // first / end A entry of the tile's columns relative to amap_ptr[front], tile columns, tile rows).
 // The CTA owns an nrows x ncols destination tile in shared memory (16 x 128 for fronts of order
 // <= 128, 8 x 256 above): zero, scatter the A
 // entries of its columns, add the children's contribution blocks one child after the other
 // (fixed order => deterministic sums, no atomics), then write the tile once (panel columns j < w
-// go to Lx, the others to CB; only rows >= column are produced).  Which children touch a column
-// block, with which of their columns and where their data lives is precomputed on the host
-// (asm_cptr / asm_ent / asm_off, no dependent pointer chasing on the device): a
-// front at the top of the tree has hundreds of small children and scanning them all per tile
-// was the whole cost of this kernel.
+// go to Lx, the others to CB; only rows >= column are produced).  Which (child, child column)
+// pairs land on a destination column and where their data lives is precomputed on the host
+// (asm_cptr / asm_ent / asm_rc / asm_off): a front at the top of the tree has hundreds of small
+// children and scanning them all per tile was the whole cost of the first version of this kernel.
 __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t* __restrict__ items, int nitems) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
@@ -257,33 +256,42 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
     }
   }
   __syncthreads();
-  // Every warp owns the destination columns j0 + warp, j0 + warp + 8 (< je) of the tile and walks
-  // the child entries on its own: a child maps at most one of its columns onto a destination
-  // column, the children are visited in order (deterministic sums) and no barrier is needed
-  // between them because no two warps touch the same column of T.
+  // Every warp owns the destination columns j0 + warp, j0 + warp + 8 (< je) of the tile.  For each
+  // of them the host has listed, in child order (deterministic sums), the (child, child column)
+  // pairs that map onto it: the lanes fetch 32 list entries and the children's descriptors at
+  // once, then the warp walks them with shuffles -- no scanning, no dependent pointer chasing,
+  // and no barrier between children because no two warps touch the same column of T.
   const bool one_chunk = m <= nrows;
-  for (int64_t e = P.asm_cptr[gcb]; e < P.asm_cptr[gcb + 1]; e++) {
-    const int ja = P.asm_ent[4 * e], jz = P.asm_ent[4 * e + 1], rc = P.asm_ent[4 * e + 2];
-    const int32_t* relc = P.rel + P.asm_off[2 * e];
-    const double* cb = P.CB + P.asm_off[2 * e + 1];
-    const int myrel = (ja + lane < jz) ? relc[ja + lane] : -1;   // jz - ja <= ncols <= 16
-    for (int J = j0 + warp; J < je; J += 8) {
-      const unsigned hit = __ballot_sync(0xffffffffu, myrel == J);
-      if (hit == 0) continue;
-      const int j = ja + __ffs(hit) - 1;
-      int ia = j, iz = rc;   // rows >= column
-      if (!one_chunk) {
-        int lo = j, hi = rc;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < i0) lo = mid + 1; else hi = mid; }
-        ia = lo;
-        hi = rc;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < ie) lo = mid + 1; else hi = mid; }
-        iz = lo;
+  for (int J = j0 + warp; J < je; J += 8) {
+    const int64_t q0 = P.asm_cptr[gcb + (J - j0)], q1 = P.asm_cptr[gcb + (J - j0) + 1];
+    double* dst = T + (J - j0) * nrows - i0;
+    for (int64_t qb = q0; qb < q1; qb += 32) {
+      const int cnt = (int)min((int64_t)32, q1 - qb);
+      int jj = 0, rcv = 0;
+      long long ro = 0, co = 0;
+      if (lane < cnt) {
+        const int ce = P.asm_ent[2 * (qb + lane)];
+        jj = P.asm_ent[2 * (qb + lane) + 1];
+        rcv = P.asm_rc[ce];
+        ro = P.asm_off[2 * ce];
+        co = P.asm_off[2 * ce + 1];
       }
-      double* dst = T + (J - j0) * nrows - i0;
-      const double* src = cb + (size_t)j * rc;
+      for (int k = 0; k < cnt; k++) {
+        const int j = __shfl_sync(0xffffffffu, jj, k), rc = __shfl_sync(0xffffffffu, rcv, k);
+        const int32_t* relc = P.rel + __shfl_sync(0xffffffffu, ro, k);
+        const double* src = P.CB + __shfl_sync(0xffffffffu, co, k) + (size_t)j * rc;
+        int ia = j, iz = rc;   // rows >= column
+        if (!one_chunk) {
+          int lo = j, hi = rc;
+          while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < i0) lo = mid + 1; else hi = mid; }
+          ia = lo;
+          hi = rc;
+          while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < ie) lo = mid + 1; else hi = mid; }
+          iz = lo;
+        }
 #pragma unroll 4
-      for (int i = ia + lane; i < iz; i += 32) dst[relc[i]] += src[i];
+        for (int i = ia + lane; i < iz; i += 32) dst[relc[i]] += src[i];
+      }
     }
   }
   __syncthreads();

@@ -23,9 +23,10 @@ struct PlanDev {
   double* dvec;
   double* dstage;         // factored diagonal blocks of the tiled fronts (NB x NB each)
   const int64_t* dsptr;   // per front: offset into dstage (tiled fronts only)
-  const int64_t* asm_cptr; // per (tiled front, destination column block): range in asm_ent
-  const int32_t* asm_ent;  // per entry: first child column, end child column, child rows below, pad
-  const int64_t* asm_off;  // per entry: offset of the child's rel[] and of its contribution block
+  const int64_t* asm_cptr; // per destination column of the tiled fronts: range in asm_ent
+  const int32_t* asm_ent;  // pairs (child descriptor, child column), in child order
+  const int32_t* asm_rc;   // per child descriptor: rows below the child's pivots (order of its contribution block)
+  const int64_t* asm_off;  // per child descriptor: offset of the child's rel[] and of its contribution block
   const int64_t* sb_ptr;   // big-front solve: per (chunk, row) CSR pointers into sb_src (SB + 1 per chunk)
   const int32_t* sb_src;   // offsets into the update-vector storage, in child order
   const int32_t* sb_flag;  // per front: offset of its block flags (big fronts only)
