@@ -111,12 +111,16 @@ __device__ __forceinline__ void panel_update(double* Pk, const int32_t* cbm, con
 __device__ __forceinline__ void ldlt8_regs(double (&g)[8][8], double (&rd)[8]) {
   B2_UNROLL
   for (int c = 0; c < 8; c++) {
-    rd[c] = __drcp_rn(g[c][c]);
+    rd[c] = rcp_nr(g[c][c]);
+    // the NEXT pivot first and with one operation after the reciprocal (its square is formed
+    // while the reciprocal is in flight): this element is the critical path of the block
+    if (c + 1 < 8) g[c + 1][c + 1] = __fma_rn(-(g[c + 1][c] * g[c + 1][c]), rd[c], g[c + 1][c + 1]);
     B2_UNROLL
     for (int r = c + 1; r < 8; r++) {
       const double lrc = g[r][c] * rd[c];
       B2_UNROLL
-      for (int t = c + 1; t <= r; t++) g[r][t] -= lrc * g[t][c];   // column c still unscaled
+      for (int t = c + 1; t <= r; t++)
+        if (!(r == c + 1 && t == c + 1)) g[r][t] -= lrc * g[t][c];   // column c still unscaled
     }
     B2_UNROLL
     for (int r = c + 1; r < 8; r++) g[r][c] *= rd[c];
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
         const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
         const int32_t* rb = P.rb_idx + P.rb_ptr[s];
         const int base = cbm[c0];
-        const double rdk = __drcp_rn(Pk[base + c0]);
+        const double rdk = rcp_nr(Pk[base + c0]);
         for (int i = lane; i < nrb; i += 32) Pk[base + rb[i]] *= rdk;
       }
       __syncthreads();

@@ -111,9 +111,10 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
   // eliminate the w pivot columns: rank-1 updates restricted to the pivot columns ...
   for (int k = 0; k < w; k++) {
     const double dk = F[k + k * m];
+    const double rdk = rcp_nr(dk);
     for (int i = k + 1 + tid; i < m; i += NT) {
       const double a = F[i + k * m];
-      const double l = a / dk;
+      const double l = a * rdk;
       ak[i] = a;
       lk[i] = l;
       F[i + k * m] = l;
@@ -200,11 +201,12 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_front_tiny(PlanDev P, const int
     const double dk = F[(k + k * m) * TNT];
     P.dvec[c0 + k] = dk;
     if (dk == 0.0) P.flags[0] = 1;
+    const double rdk = rcp_nr(dk);
     for (int j = k + 1; j < m; j++) {
-      const double lj = F[(j + k * m) * TNT] / dk;
+      const double lj = F[(j + k * m) * TNT] * rdk;
       for (int i = j; i < m; i++) F[(i + j * m) * TNT] -= F[(i + k * m) * TNT] * lj;   // column k still unscaled
     }
-    for (int i = k + 1; i < m; i++) F[(i + k * m) * TNT] /= dk;
+    for (int i = k + 1; i < m; i++) F[(i + k * m) * TNT] *= rdk;
   }
   double* Lp = P.Lx + P.lptr[s];
   for (int j = 0; j < w; j++)
@@ -334,12 +336,16 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
       B2_UNROLL
       for (int c = 0; c < 8; c++) {
         if (g[c][c] == 0.0) bad = 1;
-        rd[c] = __drcp_rn(g[c][c]);
+        rd[c] = rcp_nr(g[c][c]);
+        // the NEXT pivot first and with one operation after the reciprocal (its square is formed
+        // while the reciprocal is in flight): this element is the critical path of the block
+        if (c + 1 < 8) g[c + 1][c + 1] = __fma_rn(-(g[c + 1][c] * g[c + 1][c]), rd[c], g[c + 1][c + 1]);
         B2_UNROLL
         for (int r = c + 1; r < 8; r++) {
           const double lrc = g[r][c] * rd[c];
           B2_UNROLL
-          for (int t = c + 1; t <= r; t++) g[r][t] -= lrc * g[t][c];   // column c still unscaled
+          for (int t = c + 1; t <= r; t++)
+            if (!(r == c + 1 && t == c + 1)) g[r][t] -= lrc * g[t][c];   // column c still unscaled
         }
         B2_UNROLL
         for (int r = c + 1; r < 8; r++) g[r][c] *= rd[c];
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t*
     const int k = idx / NB, t = idx % NB;
     Lr[k * NB + t] = (t < k && k < nb) ? S[k + t * DIAG_LD] : 0.0;
   }
-  if (tid < NB) dd[tid] = (tid < nb) ? __drcp_rn(S[tid + tid * DIAG_LD]) : 1.0;   // reciprocal pivots
+  if (tid < NB) dd[tid] = (tid < nb) ? rcp_nr(S[tid + tid * DIAG_LD]) : 1.0;   // reciprocal pivots
   __syncthreads();                               // S is dead from here on: R takes its place
   B2_TICK(3);
   // TRSM_RPT rows per thread (tid, tid + TRSM_THREADS, ... of the chunk), two sets of partial sums

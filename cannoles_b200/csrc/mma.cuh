@@ -36,4 +36,22 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 #endif
 }
 
+// 1 / d on a short dependent chain: the hardware seed (MUFU.RCP64H, ~20 bits) and two Newton
+// steps (4 dependent DFMAs) -- within 1 ulp of the exact reciprocal.  __drcp_rn adds an
+// exact-rounding fix-up and a slow-path branch; the reciprocal of a pivot sits on the critical
+// path of every elimination step, where a DFMA costs ~39 cycles of latency.
+__device__ __forceinline__ double rcp_nr(double d) {
+#ifdef B2_EMULATE
+  return 1.0 / d;
+#else
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = __fma_rn(-d, x, 1.0);
+  x = __fma_rn(x, e, x);
+  e = __fma_rn(-d, x, 1.0);
+  x = __fma_rn(x, e, x);
+  return x;
+#endif
+}
+
 }  // namespace b2
