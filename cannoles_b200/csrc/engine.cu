@@ -216,31 +216,52 @@ int Engine::build_plan() {
     }
     int wmax = 0;
     for (int s : large) wmax = std::max(wmax, front_w(s));
+    if (lookahead) {   // the first diagonal blocks: nothing to overlap with yet
+      Launch D; D.kind = LK_DIAG; D.off = (int64_t)items.size(); D.jb = 0; D.flag = 1;
+      for (int s : large) { items.push_back(s); D.count++; }
+      fact_launches.push_back(D);
+    }
     for (int jb = 0; jb < wmax; jb += NB) {
       Launch T; T.kind = LK_TRSM; T.off = (int64_t)items.size(); T.jb = jb;
+      T.flag = lookahead ? 1 : 0;
+      T.join_side = (lookahead && jb > 0) ? 1 : 0;
       for (int s : large) {
         int w = front_w(s), m = front_m(s);
         if (w <= jb) continue;
         int nb = std::min(NB, w - jb);
         int nrows = m - (jb + nb);
-        int nch = std::max(1, (nrows + TRSM_ROWS - 1) / TRSM_ROWS);   // chunk 0 always exists: it owns the diagonal block
+        // without look-ahead chunk 0 always exists (it owns the diagonal block)
+        int nch = (nrows + TRSM_ROWS - 1) / TRSM_ROWS;
+        if (!lookahead) nch = std::max(1, nch);
         for (int ch = 0; ch < nch; ch++) { items.push_back(s); items.push_back(ch); T.count++; }
       }
       if (T.count) fact_launches.push_back(T);
       Launch U; U.kind = LK_UPDATE; U.off = (int64_t)items.size(); U.jb = jb; U.mode = 0;
+      U.flag = lookahead ? 1 : 0;
+      Launch D; D.kind = LK_DIAG; D.jb = jb + NB; D.flag = 0; D.side = 1;
+      std::vector<int32_t> dfronts;
       for (int s : large) {
         int w = front_w(s), m = front_m(s);
         if (w <= jb) continue;
         int nb = std::min(NB, w - jb);
         int org = jb + nb;
         if (org >= w) continue;
+        dfronts.push_back(s);
+        const bool full_next = (w - org) >= NB;   // the next pivot block fills tile (0,0) completely
         int ntj = (w - org + TILE - 1) / TILE, nti = (m - org + TILE - 1) / TILE;
         for (int tj = 0; tj < ntj; tj++)
           for (int ti = tj; ti < nti; ti++) {
+            if (lookahead && ti == 0 && tj == 0 && full_next) continue;   // k_diag owns that tile
             items.push_back(s); items.push_back(ti); items.push_back(tj); U.count++;
           }
       }
       if (U.count) fact_launches.push_back(U);
+      if (lookahead && !dfronts.empty()) {
+        D.off = (int64_t)items.size();
+        items.insert(items.end(), dfronts.begin(), dfronts.end());
+        D.count = (int)dfronts.size();
+        fact_launches.push_back(D);
+      }
     }
     {
       Launch U; U.kind = LK_UPDATE; U.off = (int64_t)items.size(); U.mode = 1;
@@ -314,6 +335,9 @@ int Engine::init(int dev) {
   for (auto& e : ev) B2_CUDA_OK(cudaEventCreate(&e));
   for (auto& e : tev) B2_CUDA_OK(cudaEventCreate(&e));
   for (auto& s : bstream) B2_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  B2_CUDA_OK(cudaStreamCreateWithFlags(&sstream, cudaStreamNonBlocking));
+  B2_CUDA_OK(cudaEventCreateWithFlags(&ev_sfork, cudaEventDisableTiming));
+  B2_CUDA_OK(cudaEventCreateWithFlags(&ev_sjoin, cudaEventDisableTiming));
   B2_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   for (auto& e : ev_join) B2_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const Symbolic& S = sym;
@@ -369,6 +393,7 @@ int Engine::init(int dev) {
   B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
   B2_CUDA_OK(cudaFuncSetAttribute(k_bwd_big, cudaFuncAttributeMaxDynamicSharedMemorySize, big - 48 * 1024));
   B2_CUDA_OK(cudaFuncSetAttribute(k_fwd<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_bwd<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -392,6 +417,9 @@ void Engine::destroy() {
   if (h_scalars) cudaFreeHost(h_scalars);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   for (auto& e : tev) if (e) cudaEventDestroy(e);
+  if (ev_sfork) cudaEventDestroy(ev_sfork);
+  if (ev_sjoin) cudaEventDestroy(ev_sjoin);
+  if (sstream) cudaStreamDestroy(sstream);
   if (ev_fork) cudaEventDestroy(ev_fork);
   for (auto& e : ev_join) if (e) cudaEventDestroy(e);
   for (auto& s : bstream) if (s) cudaStreamDestroy(s);
@@ -411,13 +439,16 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       B2_LAUNCH(k_assemble_large, L.count, 256, 0, st, plan, it, L.count);
       break;
     case LK_TRSM:
-      B2_LAUNCH(k_trsm, L.count, TRSM_THREADS, TRSM_SMEM, st, plan, it, L.count, L.jb);
+      B2_LAUNCH(k_trsm, L.count, TRSM_THREADS, TRSM_SMEM, st, plan, it, L.count, L.jb, L.flag);
+      break;
+    case LK_DIAG:
+      B2_LAUNCH(k_diag, L.count, 256, DIAG_SMEM, st, plan, it, L.count, L.jb, L.flag);
       break;
     case LK_DIAG_WRITEBACK:
       B2_LAUNCH(k_diag_writeback, L.count, 256, 0, st, plan, it, L.count);
       break;
     case LK_UPDATE:
-      B2_LAUNCH(k_update, L.count, 256, 0, st, plan, it, L.count, L.jb, NB, L.mode);
+      B2_LAUNCH(k_update, L.count, 256, 0, st, plan, it, L.count, L.jb, NB, L.mode, L.flag);
       break;
     case LK_FWD:
       if (L.cls == 0) { auto kfn = k_fwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, st, plan, it, L.count, d_x, d_upd, L.smem); }
@@ -473,15 +504,36 @@ int Engine::run_list(const std::vector<Launch>& LL, bool allow_fork) {
     const unsigned excl = mask & (1u << 8);
     mask &= ~(1u << 8);
     const bool fork = use_branches && allow_fork && !excl && (mask & (mask - 1)) != 0;
+    // a launch of the tiled chain may go to the side stream (look-ahead diagonal factorization) and
+    // a later one waits for it
+    bool side_pending = false;
+    auto chain_launch = [&](const Launch& L, cudaStream_t cs) -> int {
+      if (L.join_side && side_pending) {
+        B2_CUDA_OK(cudaStreamWaitEvent(cs, ev_sjoin, 0));
+        side_pending = false;
+      }
+      if (L.side && use_branches) {
+        B2_CUDA_OK(cudaEventRecord(ev_sfork, cs));
+        B2_CUDA_OK(cudaStreamWaitEvent(sstream, ev_sfork, 0));
+        launch_one(L, sstream);
+        B2_CUDA_OK(cudaEventRecord(ev_sjoin, sstream));
+        side_pending = true;
+      } else {
+        launch_one(L, cs);
+      }
+      return 0;
+    };
     if (!fork) {
       for (size_t q = i; q < j; q++)
-        if (LL[q].branch != 8) launch_one(LL[q], stream);
+        if (LL[q].branch != 8 && chain_launch(LL[q], stream)) return -1;
+      if (side_pending) { B2_CUDA_OK(cudaStreamWaitEvent(stream, ev_sjoin, 0)); side_pending = false; }
     } else {
       B2_CUDA_OK(cudaEventRecord(ev_fork, stream));
       for (int b = 0; b < NBRANCH; b++)
         if (mask & (1u << b)) B2_CUDA_OK(cudaStreamWaitEvent(bstream[b], ev_fork, 0));
       for (size_t q = i; q < j; q++)
-        if (LL[q].branch != 8) launch_one(LL[q], bstream[LL[q].branch]);
+        if (LL[q].branch != 8 && chain_launch(LL[q], bstream[LL[q].branch])) return -1;
+      if (side_pending) { B2_CUDA_OK(cudaStreamWaitEvent(bstream[9], ev_sjoin, 0)); side_pending = false; }
       for (int b = 0; b < NBRANCH; b++)
         if (mask & (1u << b)) {
           B2_CUDA_OK(cudaEventRecord(ev_join[b], bstream[b]));
@@ -504,7 +556,7 @@ int Engine::run_solve_launches() {
   if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
   // measured: on systems with big fronts (C4) forking the solve levels costs more than it gains
   // (3.14 -> 3.49 ms), on systems made of small fronts only (C2) it gains 25 %
-  const bool fork = nsflag == 0;
+  const bool fork = solve_fork < 0 ? nsflag == 0 : solve_fork != 0;
   if (run_list(fwd_launches, fork)) return -1;
   return run_list(bwd_launches, fork);
 }

@@ -22,6 +22,7 @@ enum LaunchKind : int {
   LK_FRONT_TINY,
   LK_FWD_TINY,
   LK_BWD_TINY,
+  LK_DIAG,
 };
 
 struct Launch {
@@ -34,6 +35,9 @@ struct Launch {
   int smem = 0;       // dynamic shared memory (bytes)
   int level = 0;      // assembly-tree level (launches of one level are independent across branches)
   int branch = 0;     // kernel family: launches of one (level, branch) are ordered, branches run concurrently
+  int flag = 0;       // k_trsm: diagonal block prefactored by k_diag; k_update: leave the next diagonal block alone; k_diag: first block
+  int side = 0;       // launch on the side stream, concurrently with what follows on the chain
+  int join_side = 0;  // wait for the side stream before this launch
 };
 
 struct Engine {
@@ -43,7 +47,14 @@ struct Engine {
   static constexpr int NBRANCH = 10;
   cudaStream_t bstream[NBRANCH] = {};   // side streams: the branches of one tree level run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[NBRANCH] = {};
+  cudaStream_t sstream = nullptr;       // side stream of the tiled chain (look-ahead diagonal factorization)
+  cudaEvent_t ev_sfork = nullptr, ev_sjoin = nullptr;
+  // look-ahead factorization of the next diagonal block on a side stream (k_diag): measured SLOWER on
+  // C4 (6.8 vs 5.5 ms: k_diag takes 40 us and the diag -> trsm chain stays serial), so off by default;
+  // B2_LOOKAHEAD=1 turns it on
+  bool lookahead = false;
   bool use_branches = true;
+  int solve_fork = -1;   // -1: fork the solve levels only when there are no big fronts; 0 / 1: force
   double small_max_m = 72;   // fronts up to this order take the shared-memory path (measured: 72 beats 128 and 40 on C4)
   int tiny_max_m = 8;        // fronts up to this order (4 / 8 classes) take the one-thread-per-front kernels
   int tiny_solve_max_m = 16; // ... and up to this order (16 / 32 classes) in the solves only (measured: 32 loses to a warp per front)

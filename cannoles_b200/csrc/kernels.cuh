@@ -422,6 +422,65 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
   }
 }
 
+// Look-ahead factorization of the diagonal block (jb, jb) of the listed fronts, one CTA each:
+// unless `first`, the block is first brought up to date with the previous pivot block,
+// A -= L(blk, prev) D L(blk, prev)^T (k_update leaves that region alone), then factored
+// (cta_ldlt64) into the staging area + dvec.  It runs on a side stream concurrently with the
+// trailing update of the previous block, so that the serial 64-pivot chain is off the critical
+// path of k_trsm.  Dynamic shared memory: DIAG_SMEM bytes.
+constexpr int DIAG_SMEM = (NB * DIAG_LD + 2 * NB * (NB + 1) + NB * 8) * (int)sizeof(double);
+__global__ void __launch_bounds__(256) k_diag(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb, int first) {
+  const int b = blockIdx.x;
+  if (b >= nitems) return;
+  const int s = items[b];
+  const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+  const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
+  if (jb >= w) return;
+  const int nb = min(NB, w - jb);
+  const double* Lp = P.Lx + P.lptr[s];
+  B2_DYN_SMEM(raw);
+  double* S = reinterpret_cast<double*>(raw);    // [NB x DIAG_LD] column-major
+  double* As = S + NB * DIAG_LD;                 // [k][i], ld NB + 1: L(jb + i, k0 + k)
+  double* Ws = As + NB * (NB + 1);               // [k][j]: L(jb + j, k0 + k) d(k0 + k)
+  double* Wd = Ws + NB * (NB + 1);               // scratch of cta_ldlt64
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int i = idx % NB, j = idx / NB;
+    S[i + j * DIAG_LD] = (i < nb && j <= i) ? Lp[(jb + i) + (size_t)(jb + j) * m] : 0.0;
+  }
+  if (!first) {
+    const int k0 = jb - NB;                      // the previous pivot block is always full
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      const int i = idx % NB, k = idx / NB;
+      const double l = (i < nb) ? Lp[(jb + i) + (size_t)(k0 + k) * m] : 0.0;
+      As[k * (NB + 1) + i] = l;
+      Ws[k * (NB + 1) + i] = l * P.dvec[c0 + k0 + k];
+    }
+    __syncthreads();
+    // thread <-> (row i, column phase): columns j = phase, phase + 4, ... <= i
+    const int i = tid & 63, phase = tid >> 6;
+    if (i < nb) {
+      for (int j = phase; j <= i; j += 4) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < NB; k += 2) {
+          a0 += As[k * (NB + 1) + i] * Ws[k * (NB + 1) + j];
+          a1 += As[(k + 1) * (NB + 1) + i] * Ws[(k + 1) * (NB + 1) + j];
+        }
+        S[i + j * DIAG_LD] -= a0 + a1;
+      }
+    }
+  }
+  __syncthreads();
+  cta_ldlt64<256>(S, nb, Wd, P.flags);
+  double* stage = P.dstage + P.dsptr[s] + (size_t)(jb / NB) * NB * NB;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int i = idx % NB, j = idx / NB;
+    if (i < nb && j <= i) stage[i + j * NB] = S[i + j * DIAG_LD];
+  }
+  if (tid < nb) P.dvec[c0 + jb + tid] = S[tid + tid * DIAG_LD];
+}
+
 // item = (front, row chunk).  Every CTA first factors the nb x nb diagonal block (jb, jb) of the
 // panel in shared memory (redundantly: a few us of work instead of one more launch on the
 // critical path; chunk 0 stores the factored block in the staging area -- NOT in the panel, which
@@ -430,7 +489,8 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
 // 8-column blocks (rolled loops, 8 x 8 unrolled bodies).
 // Dynamic shared memory: TRSM_SMEM bytes.
 constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + NB * 8 + NB) * (int)sizeof(double);
-__global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb) {
+__global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb,
+                                                       int prefact) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
   const int s = items[2 * b], chunk = items[2 * b + 1];
@@ -449,21 +509,31 @@ __global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t*
   if (tid == 0 && blockIdx.x == 0) { b2_dbg[10] = 0; b2_dbg[11] = 0; }
 #endif
   B2_TICK(0);
-  for (int idx = tid; idx < NB * NB; idx += TRSM_THREADS) {
-    const int i = idx % NB, j = idx / NB;
-    S[i + j * DIAG_LD] = (i < nb && j <= i) ? Lp[(jb + i) + (size_t)(jb + j) * m] : 0.0;
-  }
-  __syncthreads();
-  B2_TICK(1);
-  cta_ldlt64<TRSM_THREADS>(S, nb, Wd, P.flags);
-  B2_TICK(2);
-  if (chunk == 0) {
-    double* stage = P.dstage + P.dsptr[s] + (size_t)(jb / NB) * NB * NB;
+  double* stage = P.dstage + P.dsptr[s] + (size_t)(jb / NB) * NB * NB;
+  if (prefact) {
+    // look-ahead mode: k_diag has already factored this block (concurrently with the previous
+    // trailing update); it is in the staging area
     for (int idx = tid; idx < NB * NB; idx += TRSM_THREADS) {
       const int i = idx % NB, j = idx / NB;
-      if (i < nb && j <= i) stage[i + j * NB] = S[i + j * DIAG_LD];
+      S[i + j * DIAG_LD] = (i < nb && j <= i) ? stage[i + j * NB] : 0.0;
     }
-    if (tid < nb) P.dvec[c0 + jb + tid] = S[tid + tid * DIAG_LD];
+    __syncthreads();
+  } else {
+    for (int idx = tid; idx < NB * NB; idx += TRSM_THREADS) {
+      const int i = idx % NB, j = idx / NB;
+      S[i + j * DIAG_LD] = (i < nb && j <= i) ? Lp[(jb + i) + (size_t)(jb + j) * m] : 0.0;
+    }
+    __syncthreads();
+    B2_TICK(1);
+    cta_ldlt64<TRSM_THREADS>(S, nb, Wd, P.flags);
+    B2_TICK(2);
+    if (chunk == 0) {
+      for (int idx = tid; idx < NB * NB; idx += TRSM_THREADS) {
+        const int i = idx % NB, j = idx / NB;
+        if (i < nb && j <= i) stage[i + j * NB] = S[i + j * DIAG_LD];
+      }
+      if (tid < nb) P.dvec[c0 + jb + tid] = S[tid + tid * DIAG_LD];
+    }
   }
   for (int idx = tid; idx < NB * NB; idx += TRSM_THREADS) {
     const int k = idx / NB, t = idx % NB;
@@ -567,7 +637,7 @@ __global__ void __launch_bounds__(256) k_diag_writeback(PlanDev P, const int32_t
 //          (the next diagonal block is factored by the following k_trsm);
 //   mode 1 (contribution block): org = w, cols < m, C is CB (lower triangle), K = w.
 __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __restrict__ items, int nitems, int k0,
-                                                int Kreq, int mode) {
+                                                   int Kreq, int mode, int skipdiag) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
   const int s = items[3 * b], ti = items[3 * b + 1], tj = items[3 * b + 2];
@@ -579,6 +649,7 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
   if (mode == 0) { K = min(Kreq, w - k0); org = k0 + K; jend = w; }
   else { k0 = 0; K = w; org = w; jend = m; }
   const int i0 = org + ti * TILE, j0 = org + tj * TILE;
+  const int nbnext = (mode == 0) ? min(NB, w - org) : 0;   // rows of the next pivot block: [org, org + nbnext)
   constexpr int KC = UPD_KC, LDT = TILE + 4;
   __shared__ double As[2][KC][LDT];
   __shared__ double Bs[2][KC][LDT];
@@ -660,6 +731,8 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
       for (int e = 0; e < 2; e++) {
         const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
         if (ri >= m || cj >= jend || ri < cj) continue;
+        // look-ahead mode: the next diagonal block is brought up to date and factored by k_diag
+        if (skipdiag && ri < org + nbnext) continue;
         double* dst = (mode == 0) ? (Cb + ri + (size_t)cj * m) : (Cb + (ri - w) + (size_t)(cj - w) * r);
         *dst = cold[a][cc][e] - acc[a][cc][e];
       }

@@ -71,6 +71,17 @@ def test_multi_cta_solve_of_big_fronts(ctor, oracle_cls, monkeypatch, case):
     ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=order)
 
 
+def test_lookahead_diagonal_factorization_path(ctor, oracle_cls, monkeypatch):
+    """The optional look-ahead schedule (k_diag on a side stream, prefactored k_trsm, k_update that
+    leaves the next diagonal block alone) gives the same factorization."""
+    monkeypatch.setenv("B2_SMALL_MAX_M", "8")
+    monkeypatch.setenv("B2_LOOKAHEAD", "1")
+    N, r, c, v = random_kkt(60, 70, 20, 0.5, 71)
+    ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 60, 70, 20, ordering=1)
+    N, r, c, v = random_kkt(50, 60, 15, 0.3, 22)
+    ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 50, 60, 15, ordering=0)
+
+
 def test_golden_vectors(ctor):
     for name in ("mgh01con_first_kkt", "random_kkt_0", "random_kkt_1"):
         ec.check_golden(ctor, name)
