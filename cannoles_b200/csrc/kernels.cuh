@@ -810,6 +810,7 @@ __global__ void __launch_bounds__(NT * FPB) k_fwd(PlanDev P, const int32_t* __re
       double y = (lane < nb) ? xs[jb + lane] : 0.0;
       B2_UNROLL
       for (int k = 0; k < SNB; k++) {
+        if (k >= nb) break;   // uniform: most fronts are narrow (w <= 8), 32 shuffle steps would be wasted
         const double yk = __shfl_sync(0xffffffffu, y, k);
         if (lane > k) y -= lrow[k] * yk;
       }

@@ -25,6 +25,8 @@ ctor = functools.partial(B200Struct, ordering=ordering, nvar=nls.nvar, nequ=nls.
 s, rhs = first_system(nls, method, ctor)
 B = s.LDLT
 d = np.zeros(B.N)
+if not B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS):
+    s.vals[len(s.vals) - nls.nvar:] = EPS ** (1.0 / 3.0)      # the reference's first rho retry
 for _ in range(2):
     assert B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
     B.solve_ldl(rhs, d)
