@@ -82,6 +82,20 @@ def test_lookahead_diagonal_factorization_path(ctor, oracle_cls, monkeypatch):
     ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 50, 60, 15, ordering=0)
 
 
+def test_small_delta_refinement_reaches_the_bar(ctor, oracle_cls):
+    """delta = sqrt(eps): refinement sweeps are taken until the relative residual is <= 1e-12."""
+    N, r, c, v = random_kkt(40, 50, 14, 0.1, 79, delta=1.4901161193847656e-08)
+    B = ctor(N, r, c, v, nvar=40, nequ=50, ncon=14, refine_steps=3)
+    assert B.try_to_factorize(v, 40, 50, 14, EPS)
+    O = oracle_cls(N, r, c, v, perm=B.perm)
+    assert O.try_to_factorize(v, 40, 50, 14, EPS)
+    rhs = np.random.default_rng(8).standard_normal(N)
+    d = np.zeros(N)
+    B.solve_ldl(rhs, d)
+    assert B.last_relres <= ec.RESID_TOL
+    assert np.linalg.norm(O.matvec(d) + rhs) <= ec.RESID_TOL * np.linalg.norm(rhs)
+
+
 def test_golden_vectors(ctor):
     for name in ("mgh01con_first_kkt", "random_kkt_0", "random_kkt_1"):
         ec.check_golden(ctor, name)

@@ -130,3 +130,78 @@ def test_full_size_properties(ctor, cfg):
     B.solve_ldl(b2, x2)
     B.solve_ldl(2.5 * rhs + b2, x3)
     assert np.linalg.norm(x3 - (2.5 * x1 + x2)) <= 1e-9 * np.linalg.norm(x3)
+
+
+def test_small_delta_needs_refinement_and_reaches_the_bar(ctor, oracle_cls):
+    """delta = sqrt(eps) (the smallest value the loop ever uses, reference/src/CaNNOLeS.jl:52, 615):
+    pivots span 1e-8 .. 1e+1, the pivot-free factorization loses digits and the adaptive
+    refinement has to recover them: relative residual <= 1e-12 (north_star)."""
+    nv, ne, nc = 300, 400, 120
+    N, r, c, v = random_kkt(nv, ne, nc, 0.03, 77, delta=1.4901161193847656e-08)
+    B = ctor(N, r, c, v, nvar=nv, nequ=ne, ncon=nc, refine_steps=3)
+    assert B.try_to_factorize(v, nv, ne, nc, EPS)
+    O = oracle_cls(N, r, c, v, perm=B.perm)
+    assert O.try_to_factorize(v, nv, ne, nc, EPS)
+    assert B.last_inertia[:3] == O.inertia(EPS) == (nv, 0, ne + nc)
+    rhs = np.random.default_rng(8).standard_normal(N)
+    d = np.zeros(N)
+    B.solve_ldl(rhs, d)
+    assert B.last_relres <= ec.RESID_TOL
+    assert np.linalg.norm(O.matvec(d) + rhs) <= ec.RESID_TOL * np.linalg.norm(rhs)
+    assert 1 <= B.last_sweeps <= 4
+
+
+def test_gauss_newton_breakdown_takes_the_rho_retry_like_the_reference(ctor, oracle_cls):
+    """C3 slice (Gauss-Newton: zero (1,1) block).  With a fill-reducing order the rho = 0 matrix can
+    hit zero pivots; the caller protocol of newton_system! (rho0, then x100) must end in the expected
+    inertia and the retried factorization must agree with the oracle on the same order."""
+    from cannoles_b200.workloads import first_system, make_config
+    nls, method, _ = make_config("c3", 300)
+    s, rhs = first_system(nls, method, functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon, ordering=3))
+    B = s.LDLT
+    ok = B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    rho, tries = 0.0, 0
+    while not ok and tries < 6:
+        rho = EPS ** (1.0 / 3.0) if rho == 0.0 else 100.0 * rho
+        s.vals[len(s.vals) - nls.nvar:] = rho
+        ok = B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+        tries += 1
+    assert ok and B.last_inertia == (nls.nvar, 0, nls.nequ + nls.ncon, False)
+    O = oracle_cls(B.N, s.rows, s.cols, s.vals, perm=B.perm)
+    assert O.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    assert B.last_inertia[:3] == O.inertia(EPS)
+    d, do = np.zeros(B.N), np.zeros(B.N)
+    B.solve_ldl(rhs, d)
+    O.solve_ldl(rhs, do)
+    assert B.last_relres <= ec.RESID_TOL
+    assert np.linalg.norm(d - do) <= 1e-7 * np.linalg.norm(do)
+
+
+def test_inspection_entry_points(ctor, gpu_lib):
+    """b2_front_sizes / b2_profile / b2_host_register: shapes and basic invariants."""
+    import ctypes as C
+    from cannoles_b200 import _capi
+    N, r, c, v = random_kkt(120, 160, 40, 0.05, 78)
+    B = ctor(N, r, c, v, nvar=120, nequ=160, ncon=40)
+    assert B.try_to_factorize(v, 120, 160, 40, EPS)
+    d = np.zeros(N)
+    B.solve_ldl(np.ones(N), d)
+    ns = B.stats()["nsuper"]
+    w = np.zeros(ns, dtype=np.int32); m = np.zeros(ns, dtype=np.int32); lv = np.zeros(ns, dtype=np.int32)
+    assert gpu_lib.b2_front_sizes(B._h, ns, w.ctypes.data_as(_capi.p32), m.ctypes.data_as(_capi.p32),
+                                  lv.ctypes.data_as(_capi.p32)) == 0
+    assert w.sum() == N and (m >= w).all() and lv.max() + 1 == B.stats()["nlevels"]
+    MAXN = 4096
+    kinds = np.zeros(MAXN, dtype=np.int32); cls = np.zeros(MAXN, dtype=np.int32)
+    counts = np.zeros(MAXN, dtype=np.int32); ms = np.zeros(MAXN); n = C.c_int()
+    pi = C.POINTER(C.c_int)
+    for which in (0, 1):
+        assert gpu_lib.b2_profile(B._h, which, MAXN, kinds.ctypes.data_as(pi), cls.ctypes.data_as(pi),
+                                  counts.ctypes.data_as(pi), ms.ctypes.data_as(_capi.pd), C.byref(n)) == 0
+        assert n.value > 0 and (ms[:n.value] >= 0).all()
+    d2 = np.zeros(N)
+    B.solve_ldl(np.ones(N), d2)                    # the profile replays must not disturb the factor
+    assert np.array_equal(d, d2)
+    buf = np.zeros(1 << 16)
+    assert gpu_lib.b2_host_register(buf.ctypes.data_as(C.c_void_p), buf.nbytes) == 0
+    assert gpu_lib.b2_host_unregister(buf.ctypes.data_as(C.c_void_p)) == 0
