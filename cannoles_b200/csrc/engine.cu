@@ -55,6 +55,8 @@ int Engine::build_plan() {
   nsflag = 0;
   fact_launches.clear(); fwd_launches.clear(); bwd_launches.clear();
   n_small = n_large = 0;
+  int dag_tasks = 0;
+  std::vector<char> front_dag(S.nsuper, 0);
   auto front_m = [&](int s) { return (int)(S.rptr[s + 1] - S.rptr[s]); };
   auto front_w = [&](int s) { return (int)(S.scol[s + 1] - S.scol[s]); };
   std::vector<size_t> fstart, sstart, bstart;   // first launch of every level in the three lists
@@ -214,6 +216,62 @@ int Engine::build_plan() {
       }
       fact_launches.push_back(L);
     }
+    int level_np = 0;
+    for (int s : large) level_np = std::max(level_np, (front_w(s) + NB - 1) / NB);
+    // measured on C4: the dataflow launch wins where fronts have several pivot blocks (a chain of
+    // launches otherwise); levels made of thousands of one-block fronts are faster on the chain
+    if (use_dag && level_np >= dag_min_np) {
+      for (int s : large) front_dag[s] = 1;
+      // one task per NB x NB tile (I, J), I >= J, of every tiled front of the level; ticket order =
+      // column by column across the fronts (bigger fronts first), which is a topological order of
+      // the tile dependencies (see k_front_dag)
+      Launch G; G.kind = LK_DAG; G.off = (int64_t)items.size(); G.jb = ndag++;
+      struct FG { int s, nrb; int32_t fb; int m; };
+      std::vector<FG> fg;
+      int maxnrb = 0;
+      for (int s : large) {
+        int w = front_w(s), m = front_m(s);
+        int np = (w + NB - 1) / NB, nrb = np + (m - w + NB - 1) / NB;
+        if (ntflag + (int64_t)np * (nrb + 1) >= (int64_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "too many tiles"); return -1; }
+        fg.push_back({s, nrb, (int32_t)ntflag, m});
+        ntflag += (int64_t)np * (nrb + 1);   // one flag per tile of the pivot columns + one per ypre task
+        maxnrb = std::max(maxnrb, nrb);
+      }
+      std::stable_sort(fg.begin(), fg.end(), [](const FG& a, const FG& b) { return a.m > b.m; });
+      // ticket order = waves of the tile DAG over all fronts of the level (a topological order):
+      // wave 2d holds what can start once pivot block d-1 is factored -- the chain task of block d
+      // (first: it is the critical path) and the tiles of column d-1; 2d+1 the ypre task of block
+      // d+1; the tiles of the contribution block follow the last column (wave 2 np + 1)
+      struct TK { int key, pri; int32_t s, I, code, fb; };
+      std::vector<TK> tks;
+      for (const FG& f : fg) {
+        const int np = (front_w(f.s) + NB - 1) / NB;
+        for (int J = 0; J < f.nrb; J++)
+          for (int I = J; I < f.nrb; I++) {
+            if (J >= np) { tks.push_back({2 * np + 1, 1, f.s, I, J, f.fb}); continue; }
+            if (I == J) {
+              if (J == 0) tks.push_back({0, 0, f.s, 0, 0, f.fb});
+              continue;                                      // J > 0: part of the chain task of block J
+            }
+            if (I == J + 1 && I < np) {                      // chain task: tiles (I, I-1) and (I, I) ...
+              tks.push_back({2 * I, 0, f.s, I, I | (1 << 16), f.fb});
+              // ... after the task that applies the pivot blocks p < I-1 to (I, I)
+              if (I >= 2) tks.push_back({2 * (I - 1) + 1, 1, f.s, I, I | (2 << 16), f.fb});
+              continue;
+            }
+            tks.push_back({2 * (J + 1), 1, f.s, I, J, f.fb});
+          }
+      }
+      std::stable_sort(tks.begin(), tks.end(), [](const TK& a, const TK& b) { return a.key != b.key ? a.key < b.key : a.pri < b.pri; });
+      for (const TK& t : tks) {
+        items.push_back(t.s); items.push_back(t.I); items.push_back(t.code); items.push_back(t.fb);
+        G.count++;
+      }
+      G.mode = dag_tasks;   // index of its first task among all dataflow tasks (trace slots)
+      dag_tasks += G.count;
+      if (G.count) fact_launches.push_back(G);
+      continue;
+    }
     int wmax = 0;
     for (int s : large) wmax = std::max(wmax, front_w(s));
     if (lookahead) {   // the first diagonal blocks: nothing to overlap with yet
@@ -301,7 +359,8 @@ int Engine::build_plan() {
       dsptr[s] = off;
       if (front_m(s) <= (int)small_max_m) continue;
       int nblk = (front_w(s) + NB - 1) / NB;
-      for (int bi = 0; bi < nblk; bi++) { items.push_back(s); items.push_back(bi); W.count++; }
+      if (!front_dag[s])   // k_front_dag writes the diagonal blocks in place
+        for (int bi = 0; bi < nblk; bi++) { items.push_back(s); items.push_back(bi); W.count++; }
       off += (int64_t)nblk * NB * NB;
     }
     dsptr[S.nsuper] = off;
@@ -322,6 +381,7 @@ int Engine::build_plan() {
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
   if (dalloc(&d_ypub, (size_t)(2 * S.N), bytes_device)) return -1;   // forward | backward publication slots
   plan.sb_ptr = d_sb_ptr; plan.sb_src = d_sb_src; plan.sb_flag = d_sb_flag;
+  if (dalloc(&d_tflag, (size_t)(ntflag + ndag + 1), bytes_device)) return -1;
   std::reverse(bwd_launches.begin(), bwd_launches.end());
   if (upload(&d_items, items, bytes_device)) return -1;
   return 0;
@@ -388,12 +448,18 @@ int Engine::init(int dev) {
   plan.rowidx = d_rowidx; plan.rel = d_rel; plan.child_ptr = d_child_ptr; plan.child_idx = d_child_idx;
   plan.amap_ptr = d_amap_ptr; plan.amap_slot = d_amap_slot; plan.amap_pos = d_amap_pos;
   plan.nzval = d_nzval; plan.Lx = d_Lx; plan.CB = d_CB; plan.dvec = d_dvec; plan.flags = d_flags;
+  {
+    cudaDeviceProp prop;
+    B2_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    dag_ctas = 2 * prop.multiProcessorCount;   // k_front_dag: __launch_bounds__(256, 2), DAG_SMEM fits twice
+  }
   if (build_plan()) return -1;
   const int big = 200 * 1024;
   B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_front_small<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
   B2_CUDA_OK(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+  B2_CUDA_OK(cudaFuncSetAttribute(k_front_dag, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM));
   B2_CUDA_OK(cudaFuncSetAttribute(k_bwd_big, cudaFuncAttributeMaxDynamicSharedMemorySize, big - 48 * 1024));
   B2_CUDA_OK(cudaFuncSetAttribute(k_fwd<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   B2_CUDA_OK(cudaFuncSetAttribute(k_bwd<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -411,7 +477,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ypub, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ypub, d_tflag, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);
@@ -449,6 +515,10 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       break;
     case LK_UPDATE:
       B2_LAUNCH(k_update, L.count, 256, 0, st, plan, it, L.count, L.jb, NB, L.mode, L.flag);
+      break;
+    case LK_DAG:
+      B2_LAUNCH(k_front_dag, std::min(L.count, dag_ctas), 256, DAG_SMEM, st, plan, it, L.count, d_tflag,
+                d_tflag + ntflag + L.jb, L.mode);
       break;
     case LK_FWD:
       if (L.cls == 0) { auto kfn = k_fwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, st, plan, it, L.count, d_x, d_upd, L.smem); }
@@ -549,7 +619,11 @@ int Engine::run_list(const std::vector<Launch>& LL, bool allow_fork) {
   return 0;
 }
 
-int Engine::run_factor_launches() { return run_list(fact_launches, true); }
+int Engine::run_factor_launches() {
+  // tile flags and ticket counters of the dataflow launches
+  if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + ndag) * sizeof(int), stream));
+  return run_list(fact_launches, true);
+}
 
 int Engine::run_solve_launches() {
   // publication slots of the multi-CTA solves: all-ones = "not yet published" (poll_value)
@@ -565,6 +639,9 @@ int Engine::run_solve_launches() {
 extern "C" int b2_debug_clocks(long long* out64) {
   return cudaMemcpyFromSymbol(out64, b2_dbg, 64 * sizeof(long long)) == cudaSuccess ? 0 : -1;
 }
+extern "C" int b2_debug_dag_trace(long long* out, long long nlongs) {
+  return cudaMemcpyFromSymbol(out, b2_dag_trace, (size_t)nlongs * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
 #endif
 
 // Developer aid: replay the factorization (which = 0) or one forward+backward sweep (which = 1)
@@ -579,8 +656,10 @@ int Engine::profile(int which, int max, int* kinds, int* cls, int* counts, doubl
   std::vector<cudaEvent_t> evs(LL.size() + 1);
   for (auto& e : evs) B2_CUDA_OK(cudaEventCreate(&e));
   for (int rep = 0; rep < 2; rep++) {   // second pass is the warm one
-    if (which == 0) B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
-    else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
+    if (which == 0) {
+      B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
+      if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + ndag) * sizeof(int), stream));
+    } else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
     B2_CUDA_OK(cudaEventRecord(evs[0], stream));
     for (size_t i = 0; i < LL.size(); i++) {
       launch_one(*LL[i], stream);

@@ -23,6 +23,7 @@ enum LaunchKind : int {
   LK_FWD_TINY,
   LK_BWD_TINY,
   LK_DIAG,
+  LK_DAG,
 };
 
 struct Launch {
@@ -54,6 +55,14 @@ struct Engine {
   // B2_LOOKAHEAD=1 turns it on
   bool lookahead = false;
   bool use_branches = true;
+  // dataflow factorization of the tiled fronts (k_front_dag: one launch per tree level instead of a
+  // k_trsm / k_update launch pair per 64-column pivot block); B2_DAG=0 selects the launch chain
+  bool use_dag = true;
+  int dag_min_np = 4;          // ... on the tree levels whose widest front has at least this many pivot blocks (B2_DAG_MIN_NP)
+  int dag_ctas = 0;            // CTAs of a k_front_dag launch (resident CTAs of the device)
+  int64_t ntflag = 0;          // tile flags of all tiled fronts; the ticket counters of the launches follow them
+  int ndag = 0;
+  int* d_tflag = nullptr;
   int solve_fork = -1;   // -1: fork the solve levels only when there are no big fronts; 0 / 1: force
   double small_max_m = 72;   // fronts up to this order take the shared-memory path (measured: 72 beats 128 and 40 on C4)
   int tiny_max_m = 8;        // fronts up to this order (4 / 8 classes) take the one-thread-per-front kernels

@@ -310,96 +310,150 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
 }
 
 // CTA-level pivot-free LDL^T of an nb x nb block (nb <= NB = 64) held column-major in shared
-// memory (S[i + j * DIAG_LD], lower triangle), blocked in 8-column panels.  Panel step, warp 0:
-// EVERY lane factors the 8 x 8 diagonal sub-block redundantly in registers (no shuffles on the
-// pivot chain; one reciprocal per pivot instead of divisions), then substitutes its two rows of
-// the panel against it; it leaves L in S and W = L D in Wd.  Then all NT threads apply the
-// rank-8 update to the trailing columns (row-per-thread, L(i,:) in registers, W broadcast).
-// 16 barriers, small loop bodies: this runs cold, once per pivot block, on the critical path.
-// Wd: NB x 8 doubles of shared memory.  On return strict lower = L, diagonal = D.
+// memory (S[i + j * DIAG_LD], lower triangle), blocked in 8-column panels.
+// Warp 0 owns the pivot chain: EVERY lane factors the 8 x 8 diagonal sub-block redundantly in
+// registers (no shuffles, no shared memory on the chain), two pivots per step: with the current
+// 2 x 2 leading block [a b; b c] the Schur complement of both pivots is
+//     x_ij -= (p_i u_j + q_i v_j) / det,   p = c u - b v,  q = a v - b u,  det = a c - b^2,
+// where (u, v) are the two columns below the block; everything but the product with 1 / det is
+// formed while the reciprocal is in flight.  D stays diagonal: d_k = a, d_{k+1} = det / a,
+// l_{i,k} = u_i / a, l_{i,k+1} = q_i / det -- the same L D L^T as the scalar elimination.
+// Everything else is spread over the CTA (a single warp retires ~1 instruction every 4 cycles,
+// measured, so whatever stays on warp 0 is the critical path):
+//   (B) substitution of the rows below the 8 x 8 block, one row per thread (L to S, W = L D to Wd);
+//   (C) rank-8 update of the trailing block by warps 1.., while warp 0 updates only the NEXT
+//       8 x 8 diagonal block and goes straight on to factor it (look-ahead inside the CTA).
+// Two barriers per panel.  Wd: NB x 8 + 8 doubles of shared memory.
+// On return strict lower = L, diagonal = D.
+__device__ __forceinline__ double rcp_cubic(double d) {
+#ifdef B2_EMULATE
+  return 1.0 / d;
+#else
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  const double e = __fma_rn(-d, x, 1.0);      // ~2^-20
+  const double t = __fma_rn(e, e, e);         // e + e^2
+  return __fma_rn(x, t, x);                   // x (1 + e + e^2): relative error e^3
+#endif
+}
+
+// warp 0: factor the 8 x 8 block at (kb, kb) (pw <= 8 valid columns) in registers, store L8 / D
+// back into S and the reciprocal pivots into rds
+__device__ __forceinline__ void warp_ldlt8(double* S, int kb, int pw, double* rds, int* flags) {
+  constexpr int ld = DIAG_LD;
+  double g[8][8], rd[8];
+  B2_UNROLL
+  for (int c = 0; c < 8; c++)
+    B2_UNROLL
+    for (int t = 0; t <= c; t++) g[c][t] = (c < pw) ? S[(kb + c) + (kb + t) * ld] : (c == t ? 1.0 : 0.0);
+  bool bad = false;
+  B2_UNROLL
+  for (int k = 0; k < 8; k += 2) {
+    const double a = g[k][k], b = g[k + 1][k], c = g[k + 1][k + 1];
+    const double det = __fma_rn(a, c, -(b * b));
+    bad = bad || a == 0.0 || det == 0.0;
+    const double rdet = rcp_cubic(det);
+    const double ra = rcp_nr(a);
+    double p[8], q[8];
+    B2_UNROLL
+    for (int i = k + 2; i < 8; i++) {
+      p[i] = __fma_rn(c, g[i][k], -(b * g[i][k + 1]));
+      q[i] = __fma_rn(a, g[i][k + 1], -(b * g[i][k]));
+    }
+    B2_UNROLL
+    for (int i = k + 2; i < 8; i++)
+      B2_UNROLL
+      for (int j = k + 2; j <= i; j++) {
+        const double num = __fma_rn(p[i], g[j][k], q[i] * g[j][k + 1]);
+        g[i][j] = __fma_rn(-num, rdet, g[i][j]);
+      }
+    B2_UNROLL
+    for (int i = k + 2; i < 8; i++) { g[i][k] *= ra; g[i][k + 1] = q[i] * rdet; }
+    g[k + 1][k] = b * ra;
+    g[k + 1][k + 1] = det * ra;
+    rd[k] = ra;
+    rd[k + 1] = a * rdet;
+  }
+  __syncwarp();   // every lane has read the unfactored block before anyone overwrites it
+  // every lane holds the same values: same-address stores, one of them lands
+  B2_UNROLL
+  for (int c = 0; c < 8; c++) {
+    if (c < pw) {
+      B2_UNROLL
+      for (int t = 0; t <= c; t++) S[(kb + c) + (kb + t) * ld] = g[c][t];
+      rds[c] = rd[c];
+    }
+  }
+  if (bad && (threadIdx.x & 31) == 0) flags[0] = 1;
+}
+
 template <int NT>
 __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* flags) {
   constexpr int ld = DIAG_LD;
+  static_assert(NT >= 64, "cta_ldlt64 needs a pivot warp and at least one update warp");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* rds = Wd + NB * 8;
+  if (warp == 0) warp_ldlt8(S, 0, min(8, nb), rds, flags);
   for (int kb = 0; kb < nb; kb += 8) {
 #ifdef B2_TIMING
     long long tp0 = clock64();
 #endif
     const int pw = min(8, nb - kb);
-    if (warp == 0) {
-      double g[8][8], rd[8];
+    const int t0 = kb + 8;
+    __syncthreads();                    // L8 / 1/d of this panel are in S / rds; the trailing block is up to date
+    // (B) rows below the 8 x 8 block: w[c] = a[c] - sum_{t<c} w[t] L8[c][t],  l[c] = w[c] / d_c
+    for (int row = t0 + tid; row < nb; row += NT) {
+      double wv[8];
       B2_UNROLL
-      for (int c = 0; c < 8; c++)
+      for (int c = 0; c < 8; c++) wv[c] = (c < pw) ? S[row + (kb + c) * ld] : 0.0;
+      B2_UNROLL
+      for (int c = 1; c < 8; c++)
         B2_UNROLL
-        for (int t = 0; t <= c; t++) g[c][t] = (c < pw) ? S[(kb + c) + (kb + t) * ld] : (c == t ? 1.0 : 0.0);
-      int bad = 0;
+        for (int t = 0; t < c; t++) wv[c] -= wv[t] * ((c < pw) ? S[(kb + c) + (kb + t) * ld] : 0.0);
       B2_UNROLL
       for (int c = 0; c < 8; c++) {
-        if (g[c][c] == 0.0) bad = 1;
-        rd[c] = rcp_nr(g[c][c]);
-        // the NEXT pivot first and with one operation after the reciprocal (its square is formed
-        // while the reciprocal is in flight): this element is the critical path of the block
-        if (c + 1 < 8) g[c + 1][c + 1] = __fma_rn(-(g[c + 1][c] * g[c + 1][c]), rd[c], g[c + 1][c + 1]);
-        B2_UNROLL
-        for (int r = c + 1; r < 8; r++) {
-          const double lrc = g[r][c] * rd[c];
-          B2_UNROLL
-          for (int t = c + 1; t <= r; t++)
-            if (!(r == c + 1 && t == c + 1)) g[r][t] -= lrc * g[t][c];   // column c still unscaled
-        }
-        B2_UNROLL
-        for (int r = c + 1; r < 8; r++) g[r][c] *= rd[c];
+        if (c < pw) { S[row + (kb + c) * ld] = wv[c] * rds[c]; Wd[row * 8 + c] = wv[c]; }
+        else Wd[row * 8 + c] = 0.0;
       }
-      // now g[c][t] (t < c) = L8, g[c][c] = d_c.  Rows kb + lane and kb + 32 + lane of the panel:
-      // w[c] = a[c] - sum_{t<c} w[t] L8[c][t],  l[c] = w[c] / d_c
-      double wv2[2][8];
-      B2_UNROLL
-      for (int h = 0; h < 2; h++) {
-        const int row = kb + 32 * h + lane;
-        B2_UNROLL
-        for (int c = 0; c < 8; c++)
-          wv2[h][c] = (row < nb && c < pw && kb + c <= row) ? S[row + (kb + c) * ld] : 0.0;
-      }
-      __syncwarp();   // every lane has read the unfactored block before anyone overwrites it
-      B2_UNROLL
-      for (int h = 0; h < 2; h++) {
-        const int row = kb + 32 * h + lane;
-        double* wv = wv2[h];
-        B2_UNROLL
-        for (int c = 1; c < 8; c++)
-          B2_UNROLL
-          for (int t = 0; t < c; t++) wv[c] -= wv[t] * g[c][t];
-        B2_UNROLL
-        for (int c = 0; c < 8; c++) {
-          if (row < nb && c < pw) {
-            if (kb + c < row) { S[row + (kb + c) * ld] = wv[c] * rd[c]; Wd[row * 8 + c] = wv[c]; }
-            else if (kb + c == row) S[row + row * ld] = g[c][c];
-          }
-        }
-      }
-      if (bad && lane == 0) flags[0] = 1;
     }
-    __syncthreads();
+    __syncthreads();                    // panel kb complete
     B2_ACC(10, tp0);
 #ifdef B2_TIMING
     tp0 = clock64();
 #endif
-    const int t0 = kb + 8;
-    if (t0 < nb) {
-      // S(i,j) -= sum_c L(i,c) W(j,c), t0 <= j <= i < nb.  Thread <-> (row pair, column phase):
-      // rows t0 + p and nb - 1 - p together have nb - t0 + 1 columns whatever p, so the triangle
-      // is balanced; the NT / 32 phases take every (NT/32)-th column.  W(j,:) is a broadcast read.
-      const int n = nb - t0;
-      const int p = tid & 31, phase = tid >> 5;
-      constexpr int NPH = NT / 32;
-      const int iA = t0 + p, iB = nb - 1 - p;
-      if (p < (n + 1) / 2) {
+    if (t0 >= nb) break;
+    if (warp == 0) {
+      // the next 8 x 8 diagonal block only: lane <-> (row i, columns 2 jp, 2 jp + 1), then its LDL^T
+      const int i = t0 + (lane >> 2), j = t0 + 2 * (lane & 3);
+      if (i < nb) {
+        double s0 = 0.0, s1 = 0.0;
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) {
+          const double l = S[i + (kb + c) * ld];
+          s0 += l * Wd[j * 8 + c];
+          s1 += l * Wd[(j + 1) * 8 + c];     // j + 1 <= t0 + 7 < NB: in bounds, unused when beyond the row
+        }
+        if (j <= i) S[i + j * ld] -= s0;
+        if (j + 1 <= i) S[i + (j + 1) * ld] -= s1;
+      }
+      __syncwarp();
+      warp_ldlt8(S, t0, min(8, nb - t0), rds, flags);
+    } else {
+      // (C) rows t0 + 8 .. nb - 1, columns t0 .. row.  Thread <-> (row pair, column phase): rows
+      // t1 + p and nb - 1 - p together have the same number of columns whatever p, so the
+      // trapezoid is balanced; the phases (one per warp) take every NPH-th column.
+      const int t1 = t0 + 8;
+      const int n = nb - t1;
+      const int p = lane, phase = warp - 1;
+      constexpr int NPH = NT / 32 - 1;
+      const int iA = t1 + p, iB = nb - 1 - p;
+      if (n > 0 && p < (n + 1) / 2) {
         const bool two = iB > iA;
         double la[8], lb[8];
         B2_UNROLL
         for (int c = 0; c < 8; c++) {
-          la[c] = (c < pw) ? S[iA + (kb + c) * ld] : 0.0;
-          lb[c] = (c < pw && two) ? S[iB + (kb + c) * ld] : 0.0;
+          la[c] = S[iA + (kb + c) * ld];
+          lb[c] = two ? S[iB + (kb + c) * ld] : 0.0;
         }
         const int jmax = two ? iB : iA;
 #pragma unroll 2
@@ -417,7 +471,6 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
         }
       }
     }
-    __syncthreads();
     B2_ACC(11, tp0);
   }
 }
@@ -428,7 +481,7 @@ __device__ __forceinline__ void cta_ldlt64(double* S, int nb, double* Wd, int* f
 // (cta_ldlt64) into the staging area + dvec.  It runs on a side stream concurrently with the
 // trailing update of the previous block, so that the serial 64-pivot chain is off the critical
 // path of k_trsm.  Dynamic shared memory: DIAG_SMEM bytes.
-constexpr int DIAG_SMEM = (NB * DIAG_LD + 2 * NB * (NB + 1) + NB * 8) * (int)sizeof(double);
+constexpr int DIAG_SMEM = (NB * DIAG_LD + 2 * NB * (NB + 1) + 2 * NB * 8) * (int)sizeof(double);
 __global__ void __launch_bounds__(256) k_diag(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb, int first) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
@@ -488,7 +541,7 @@ __global__ void __launch_bounds__(256) k_diag(PlanDev P, const int32_t* __restri
 // L21 = A21 L11^{-T} D^{-1} for its TRSM_ROWS rows below the block: TRSM_RPT rows per thread, rows staged in shared memory, substitution in
 // 8-column blocks (rolled loops, 8 x 8 unrolled bodies).
 // Dynamic shared memory: TRSM_SMEM bytes.
-constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + NB * 8 + NB) * (int)sizeof(double);
+constexpr int TRSM_SMEM = (NB * TRSM_ROWS + NB * NB + 2 * NB * 8 + NB) * (int)sizeof(double);
 __global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t* __restrict__ items, int nitems, int jb,
                                                        int prefact) {
   const int b = blockIdx.x;
@@ -502,8 +555,8 @@ __global__ void __launch_bounds__(TRSM_THREADS) k_trsm(PlanDev P, const int32_t*
   double* R = reinterpret_cast<double*>(raw);   // [NB][TRSM_ROWS]; its head doubles as the diagonal block S
   double* S = R;                                // [NB x DIAG_LD] column-major (NB*DIAG_LD <= NB*TRSM_ROWS)
   double* Lr = R + NB * TRSM_ROWS;              // [NB][NB] row-major copy of L11 (strict lower)
-  double* Wd = Lr + NB * NB;                    // [NB][8] scratch of cta_ldlt64
-  double* dd = Wd + NB * 8;
+  double* Wd = Lr + NB * NB;                    // [2][NB][8] scratch of cta_ldlt64
+  double* dd = Wd + 2 * NB * 8;
   const int tid = threadIdx.x;
 #ifdef B2_TIMING
   if (tid == 0 && blockIdx.x == 0) { b2_dbg[10] = 0; b2_dbg[11] = 0; }
@@ -737,6 +790,398 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
         *dst = cold[a][cc][e] - acc[a][cc][e];
       }
   B2_TICK(23);
+}
+
+// ------------------------------------------------------------------------------------------
+// (2d) Dataflow factorization of the tiled fronts of one tree level: ONE launch replaces the
+// k_trsm / k_update / k_diag_writeback launch chain (two launches per 64-column pivot block on
+// the critical path).  The front is cut into NB x NB tiles: row/column blocks 0 .. np-1 are the
+// pivot blocks, np .. np+nq-1 the blocks of the contribution block (which starts at row w,
+// not at a multiple of NB).  A plain task is one tile (I, J), I >= J, left-looking:
+//     C(I,J) -= sum_{p < min(J, np)} L(I,p) D_p L(J,p)^T        (FP64 DMMA, operands via L2)
+//     J < np, I == J : pivot-free LDL^T of the tile (cta_ldlt64), write L/D in place, publish
+//                      the inverses of its eight 8 x 8 unit-lower diagonal blocks + 1/d
+//     J < np, I >  J : L(I,J) = C L(J,J)^{-T} D^{-1} by block substitution in DMMA fragments
+//     J >= np        : the tile of the contribution block is complete
+// The tiles (J, J-1) and (J, J) of a pivot block J >= 1 form ONE task (a "chain" task): both are
+// brought up to date with the pivot blocks p < J-1 ahead of time; when block J-1 is factored the
+// task substitutes (J, J-1), applies that last update to (J, J) straight from shared memory and
+// factors it -- the chain diag(J-1) -> diag(J) stays on one SM, with one flag hop.
+// Every tile of a pivot column has a flag in global memory, raised when its final L is
+// visible; a task waits per p for flag(I,p) and flag(J,p), so the pivot block p+1 is factored
+// as soon as ITS tiles are up to date while the rest of the trailing update is still running
+// on other SMs (look-ahead without a scheduler).  CTAs take tasks from a ticket counter in a
+// host-built topological order (column by column): a CTA only waits for tasks with a smaller
+// ticket, which are running or done, so the waits cannot deadlock whatever the number of
+// resident CTAs.  The accumulation order per tile is fixed (p ascending): results do not depend
+// on the schedule.  The diagonal tile of a chain task is brought up to date with p < J-1 by a
+// third kind of task ("ypre", on another SM) that hands it over through the panel.
+// task item = (front, I, J | kind << 16, first flag of the front), kind 0 plain, 1 chain, 2 ypre.
+// ------------------------------------------------------------------------------------------
+#ifdef B2_TIMING
+constexpr int DAG_TRACE_MAX = 1 << 16;
+constexpr int DAG_TRACE_W = 12;
+__device__ long long b2_dag_trace[DAG_TRACE_W * DAG_TRACE_MAX];
+__device__ __forceinline__ long long dag_now() { long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; }
+#define DAG_TRACE(slot) do { if (tid == 0 && trace_base + tk < DAG_TRACE_MAX) b2_dag_trace[DAG_TRACE_W * (trace_base + tk) + (slot)] = dag_now(); } while (0)
+#else
+#define DAG_TRACE(slot)
+#endif
+constexpr int DAG_LDT = TILE + 4;
+constexpr int DAG_LDL = NB + 1;
+constexpr int DAG_SMEM = (4 * UPD_KC * DAG_LDT + NB * DAG_LDT + NB * DAG_LDL + 8 * 64 + NB) * (int)sizeof(double);
+
+__device__ __forceinline__ int dag_peek(const int* f) {
+#ifdef B2_EMULATE
+  return *f;
+#else
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void dag_wait(const int* f) {
+#ifdef B2_EMULATE
+  // the emulator runs the tasks one after the other in ticket order: the producer must be done
+  if (*f == 0) { fprintf(stderr, "k_front_dag: wait on a task that has not run\n"); abort(); }
+#else
+  while (dag_peek(f) == 0) __nanosleep(20);
+#endif
+}
+__device__ __forceinline__ void dag_raise(int* f) {
+#ifdef B2_EMULATE
+  *f = 1;
+#else
+  __threadfence();
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+#endif
+}
+// operands written by other CTAs of the same launch: read through L2
+__device__ __forceinline__ double dag_ld(const double* p) {
+#ifdef B2_EMULATE
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+// C fragment (c0, c1 = C[g][2t], C[g][2t+1]) -> A fragment of its K-step h: A[g][4h + t]
+__device__ __forceinline__ double frag_c2a(double c0, double c1, int h, int lane) {
+  const int src = (lane & ~3) | (2 * h + ((lane & 3) >> 1));
+  const double v0 = __shfl_sync(0xffffffffu, c0, src), v1 = __shfl_sync(0xffffffffu, c1, src);
+  return (lane & 1) ? v1 : v0;
+}
+
+__global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* __restrict__ items, int ntasks,
+                                                      int* __restrict__ tflag, int* __restrict__ ticket, int trace_base) {
+  constexpr int KC = UPD_KC, LDT = DAG_LDT, LDL = DAG_LDL;
+  B2_DYN_SMEM(raw);
+  double* As = reinterpret_cast<double*>(raw);   // [2][KC][LDT]
+  double* Bs = As + 2 * KC * LDT;                // [2][KC][LDT]   (As | Bs = NB x LDT: W of a chain task)
+  double* T = Bs + 2 * KC * LDT;                 // the tile after the update: [col][row] ld LDT (substitution) / [row + col * DIAG_LD] (LDL^T)
+  double* Lr = T + NB * LDT;                     // L(J,J) row-major, ld LDL (substitution) / scratch of cta_ldlt64
+  double* Mi = Lr + NB * LDL;                    // inverses of the 8 x 8 diagonal blocks of L(J,J), row-major
+  double* rdv = Mi + 8 * 64;                     // 1 / d of the pivot block
+  __shared__ int s_tk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = warp & 1, wc = warp >> 1;       // warp tile of the update: rows wr*32.., cols wc*16..
+  const int lr = tid & 63, lk = tid >> 6;
+  for (;;) {
+    __syncthreads();                             // the previous task is done with shared memory and s_tk
+    if (tid == 0) s_tk = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tk = s_tk;
+    if (tk >= ntasks) break;
+    const int s = items[4 * tk], I = items[4 * tk + 1], fb = items[4 * tk + 3];
+    const int J = items[4 * tk + 2] & 0xffff;
+    const int kind = items[4 * tk + 2] >> 16;
+    const bool chain = kind == 1;                // I == J >= 1: tiles (J, J-1) and (J, J)
+    const bool ypre = kind == 2;                 // I == J >= 2: tile (J, J) up to date with the pivot blocks p < J-1
+#ifdef B2_TIMING
+    if (tid == 0 && trace_base + tk < DAG_TRACE_MAX) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      b2_dag_trace[DAG_TRACE_W * (trace_base + tk) + 0] = ((long long)s << 32) | (chain ? (1 << 30) : 0) | (I << 15) | J;
+      b2_dag_trace[DAG_TRACE_W * (trace_base + tk) + 1] = smid;
+    }
+#endif
+    DAG_TRACE(2);
+    const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+    const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
+    const int r = m - w;
+    const int np = (w + NB - 1) / NB, nrb = np + (r + NB - 1) / NB;
+    const int i0 = I < np ? I * NB : w + (I - np) * NB, iend = I < np ? min(i0 + NB, w) : min(i0 + NB, m);
+    const bool pivcol = J < np;
+    double* Lp = P.Lx + P.lptr[s];
+    double acc[4][2][2];
+    // ---- the update(s): one tile, or (J, J-1) then (J, J) of a chain task ------------------
+    for (int ph = 0; ph < (chain ? 2 : 1); ph++) {
+      const int Jt = (chain && ph == 0) ? J - 1 : J;            // column block of this tile
+      const int j0 = Jt < np ? Jt * NB : w + (Jt - np) * NB, jend = Jt < np ? min(j0 + NB, w) : min(j0 + NB, m);
+      // pivot columns applied here (a chain task takes its diagonal tile from the ypre task)
+      const int Ktot = chain ? (ph == 0 ? (J - 1) * NB : 0) : (ypre ? (J - 1) * NB : (pivcol ? J * NB : w));
+      const bool from_ypre = chain && ph == 1 && J >= 2;
+      if (from_ypre) {
+        if (tid == 0) dag_wait(tflag + fb + np * nrb + J);
+        __syncthreads();
+      }
+      const int* fI = tflag + fb + I;            // flag of tile (I, p): fI[p * nrb]
+      const int* fJ = tflag + fb + Jt;
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int c = 0; c < 2; c++) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
+      // the tile as the extend-add left it (a previous launch): read now, used after the K loop
+      double cold[4][2][2];
+      const double* Cb = pivcol ? Lp : (P.CB + P.cbptr[s]);
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int cc = 0; cc < 2; cc++)
+          B2_UNROLL
+          for (int e = 0; e < 2; e++) {
+            const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
+            const bool ok = ri < iend && cj < jend && ri >= cj;
+            const double* src = pivcol ? (Cb + ri + (size_t)cj * m) : (Cb + (ri - w) + (size_t)(cj - w) * r);
+            cold[a][cc][e] = ok ? (from_ypre ? dag_ld(src) : *src) : 0.0;
+          }
+      const int nchunk = (Ktot + KC - 1) / KC;
+      if (nchunk > 0) {
+        const int gi = i0 + lr, gj = j0 + lr;
+        const bool vi = gi < iend, vj = gj < jend;
+        const double* pa = Lp + gi;
+        const double* pb = Lp + gj;
+        const double* dv = P.dvec + c0;
+        double ra[KC / 4], rb[KC / 4];
+        auto gload = [&](int kc) {
+          B2_UNROLL
+          for (int p = 0; p < KC / 4; p++) {
+            const int k = kc + lk + 4 * p;
+            ra[p] = (vi && k < Ktot) ? dag_ld(pa + (size_t)k * m) : 0.0;
+            rb[p] = (vj && k < Ktot) ? dag_ld(pb + (size_t)k * m) * dag_ld(dv + k) : 0.0;
+          }
+        };
+        auto sstore = [&](int buf) {
+          B2_UNROLL
+          for (int p = 0; p < KC / 4; p++) {
+            As[(buf * KC + lk + 4 * p) * LDT + lr] = ra[p];
+            Bs[(buf * KC + lk + 4 * p) * LDT + lr] = rb[p];
+          }
+        };
+        if (tid == 0) { dag_wait(fI); dag_wait(fJ); }
+        __syncthreads();
+        gload(0);
+        sstore(0);
+        __syncthreads();
+        for (int c = 0; c < nchunk; c++) {
+          const int buf = c & 1;
+          const bool more = c + 1 < nchunk;
+          const int kn = (c + 1) * KC;
+          bool pre = more;
+          if (more && (kn % NB) == 0) {          // the next chunk starts a new pivot block: is it there yet?
+            const int pn = kn / NB;
+            pre = __syncthreads_and(dag_peek(fI + pn * nrb) != 0 && dag_peek(fJ + pn * nrb) != 0) != 0;
+          }
+          if (pre) gload(kn);
+          B2_UNROLL
+          for (int ks = 0; ks < KC; ks += 4) {
+            double af[4], bf[2];
+            B2_UNROLL
+            for (int a = 0; a < 4; a++) af[a] = As[(buf * KC + ks + t) * LDT + wr * 32 + a * 8 + g];
+            B2_UNROLL
+            for (int cc = 0; cc < 2; cc++) bf[cc] = Bs[(buf * KC + ks + t) * LDT + wc * 16 + cc * 8 + g];
+            B2_UNROLL
+            for (int a = 0; a < 4; a++)
+              B2_UNROLL
+              for (int cc = 0; cc < 2; cc++) dmma_8x8x4(acc[a][cc][0], acc[a][cc][1], af[a], bf[cc]);
+          }
+          if (more) {
+            if (!pre) {                          // not yet: wait now that the chunk in hand is consumed
+              const int pn = kn / NB;
+              if (tid == 0) { dag_wait(fI + pn * nrb); dag_wait(fJ + pn * nrb); }
+              __syncthreads();
+              gload(kn);
+            }
+            sstore(buf ^ 1);
+          }
+          __syncthreads();
+        }
+      }
+      // from here on acc = -(updated tile): the original tile is folded in (frees its registers)
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int cc = 0; cc < 2; cc++) { acc[a][cc][0] -= cold[a][cc][0]; acc[a][cc][1] -= cold[a][cc][1]; }
+      if (pivcol && I > Jt) {                    // rows below a pivot block: to shared memory for the substitution
+        B2_UNROLL
+        for (int a = 0; a < 4; a++)
+          B2_UNROLL
+          for (int cc = 0; cc < 2; cc++)
+            B2_UNROLL
+            for (int e = 0; e < 2; e++) {
+              const int li = wr * 32 + a * 8 + g, lj = wc * 16 + cc * 8 + 2 * t + e;
+              T[lj * LDT + li] = -acc[a][cc][e];
+            }
+      }
+    }
+    DAG_TRACE(3);
+    if (ypre) {                                  // hand the partially updated diagonal tile over through the panel
+      const int j0 = J * NB, jend = min(j0 + NB, w);
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int cc = 0; cc < 2; cc++)
+          B2_UNROLL
+          for (int e = 0; e < 2; e++) {
+            const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
+            if (ri < iend && cj < jend && ri >= cj) Lp[ri + (size_t)cj * m] = -acc[a][cc][e];
+          }
+      __syncthreads();
+      if (tid == 0) dag_raise(tflag + fb + np * nrb + J);
+      DAG_TRACE(9);
+      continue;
+    }
+    if (!pivcol) {                               // contribution block: done
+      const int j0 = w + (J - np) * NB, jend = min(j0 + NB, m);
+      double* Cb = P.CB + P.cbptr[s];
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int cc = 0; cc < 2; cc++)
+          B2_UNROLL
+          for (int e = 0; e < 2; e++) {
+            const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
+            if (ri < iend && cj < jend && ri >= cj) Cb[(ri - w) + (size_t)(cj - w) * r] = -acc[a][cc][e];
+          }
+      DAG_TRACE(9);
+      continue;
+    }
+    if (chain || I > J) {
+      // ---- substitution against pivot block Js: W = C L(Js,Js)^{-T} in 8-column blocks, right-
+      // looking inside the tile; warp <-> 8 rows, the eight 8 x 8 blocks of its rows live in C
+      // fragments.  L(I,Js) = W D^{-1} goes to the panel; a chain task also keeps W (in As|Bs) and
+      // W D^{-1} (in T) for the update of its diagonal tile.
+      const int Js = chain ? J - 1 : J;
+      const int js0 = Js * NB, nbs = min(NB, w - js0);
+      const double* stage = P.dstage + P.dsptr[s] + (size_t)Js * NB * NB;
+      int* fS = tflag + fb + Js * nrb;           // flags of column Js
+      if (tid == 0) dag_wait(fS + Js);
+      __syncthreads();
+      DAG_TRACE(4);
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx % NB, j = idx / NB;
+        Lr[i * LDL + j] = (j < i && i < nbs) ? dag_ld(Lp + (js0 + i) + (size_t)(js0 + j) * m) : 0.0;
+      }
+      for (int idx = tid; idx < 8 * 64; idx += 256) Mi[idx] = dag_ld(stage + idx);
+      if (tid < NB) rdv[tid] = dag_ld(stage + 512 + tid);
+      __syncthreads();
+      DAG_TRACE(5);
+      {
+        const int row = warp * 8 + g;
+        double cf[8][2];
+        B2_UNROLL
+        for (int kb = 0; kb < 8; kb++) {
+          cf[kb][0] = T[(kb * 8 + 2 * t) * LDT + row];
+          cf[kb][1] = T[(kb * 8 + 2 * t + 1) * LDT + row];
+        }
+        __syncwarp();                            // T rows of this warp are rewritten below (chain)
+        const int gi = i0 + row;
+        B2_UNROLL
+        for (int kb = 0; kb < 8; kb++) {
+          const double a0 = frag_c2a(cf[kb][0], cf[kb][1], 0, lane), a1 = frag_c2a(cf[kb][0], cf[kb][1], 1, lane);
+          double w0 = 0.0, w1 = 0.0;
+          dmma_8x8x4(w0, w1, a0, Mi[kb * 64 + g * 8 + t]);
+          dmma_8x8x4(w0, w1, a1, Mi[kb * 64 + g * 8 + 4 + t]);
+          if (kb < 7) {
+            const double n0 = -frag_c2a(w0, w1, 0, lane), n1 = -frag_c2a(w0, w1, 1, lane);
+            B2_UNROLL
+            for (int k2 = kb + 1; k2 < 8; k2++) {
+              dmma_8x8x4(cf[k2][0], cf[k2][1], n0, Lr[(k2 * 8 + g) * LDL + kb * 8 + t]);
+              dmma_8x8x4(cf[k2][0], cf[k2][1], n1, Lr[(k2 * 8 + g) * LDL + kb * 8 + 4 + t]);
+            }
+          }
+          B2_UNROLL
+          for (int e = 0; e < 2; e++) {
+            const int lc = kb * 8 + 2 * t + e;
+            const double wv = e ? w1 : w0, lv = wv * rdv[lc];
+            if (gi < iend && lc < nbs) Lp[gi + (size_t)(js0 + lc) * m] = lv;
+            if (chain) { As[lc * LDT + row] = wv; T[lc * LDT + row] = lv; }
+          }
+        }
+      }
+      __syncthreads();
+      DAG_TRACE(6);
+      if (!chain) {
+        if (tid == 0) dag_raise(fS + I);
+        DAG_TRACE(9);
+        continue;
+      }
+      // warps 4 and 6 own the sub-tiles strictly above the diagonal of (J, J): nothing to update
+      if (tid == 6 * 32) dag_raise(fS + I);
+      if (warp != 4 && warp != 6) {
+        for (int ks = 0; ks < NB; ks += 4) {
+          double af[4], bf[2];
+          B2_UNROLL
+          for (int a = 0; a < 4; a++) af[a] = As[(ks + t) * LDT + wr * 32 + a * 8 + g];
+          B2_UNROLL
+          for (int cc = 0; cc < 2; cc++) bf[cc] = T[(ks + t) * LDT + wc * 16 + cc * 8 + g];
+          B2_UNROLL
+          for (int a = 0; a < 4; a++)
+            B2_UNROLL
+            for (int cc = 0; cc < 2; cc++) dmma_8x8x4(acc[a][cc][0], acc[a][cc][1], af[a], bf[cc]);
+        }
+      }
+      __syncthreads();                           // everybody is done reading T
+    }
+    // ---- pivot-free LDL^T of the diagonal tile (J, J) ----------------------------------------
+    {
+      const int j0 = J * NB, nb = min(NB, w - j0);
+      double* stage = P.dstage + P.dsptr[s] + (size_t)J * NB * NB;
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int cc = 0; cc < 2; cc++)
+          B2_UNROLL
+          for (int e = 0; e < 2; e++) {
+            const int li = wr * 32 + a * 8 + g, lj = wc * 16 + cc * 8 + 2 * t + e;
+            if (li >= lj) T[li + lj * DIAG_LD] = -acc[a][cc][e];
+          }
+      __syncthreads();
+      DAG_TRACE(7);
+      cta_ldlt64<256>(T, nb, Lr, P.flags);
+      DAG_TRACE(8);
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx % NB, j = idx / NB;
+        if (i < nb && j <= i) Lp[(j0 + i) + (size_t)(j0 + j) * m] = T[i + j * DIAG_LD];
+      }
+      if (tid < nb) P.dvec[c0 + j0 + tid] = T[tid + tid * DIAG_LD];
+      if (tid < 64) {
+        // column jc of the inverse of the unit-lower 8 x 8 diagonal block kb (identity beyond nb)
+        const int kb = tid >> 3, jc = tid & 7;
+        double x[8];
+        B2_UNROLL
+        for (int i = 0; i < 8; i++) x[i] = (i == jc) ? 1.0 : 0.0;
+        B2_UNROLL
+        for (int i = 1; i < 8; i++) {
+          double sum = 0.0;
+          B2_UNROLL
+          for (int tt = 0; tt < i; tt++) {
+            const double l = (kb * 8 + i < nb) ? T[(kb * 8 + i) + (kb * 8 + tt) * DIAG_LD] : 0.0;
+            sum += l * x[tt];
+          }
+          if (i > jc) x[i] = -sum;
+        }
+        B2_UNROLL
+        for (int i = 0; i < 8; i++) stage[kb * 64 + i * 8 + jc] = x[i];
+      } else if (tid < 128) {
+        const int c = tid - 64;
+        stage[512 + c] = (c < nb) ? rcp_nr(T[c + c * DIAG_LD]) : 1.0;
+      }
+      __syncthreads();
+      if (tid == 0) dag_raise(tflag + fb + J * nrb + J);
+      DAG_TRACE(9);
+    }
+  }
 }
 
 // pivot-sign counts (src/solver_types.jl:90-96): counts[0] = #{d > tol}, [1] = #{|d| <= tol},

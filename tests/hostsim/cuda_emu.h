@@ -198,6 +198,16 @@ inline void launch(F kernel, dim3 grid, dim3 block, size_t smem, Args... args) {
 
 inline void __syncthreads() { emu::block_barrier(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
+inline int __syncthreads_and(int pred) {
+  static int acc;
+  emu::block_barrier();
+  if (emu::S().cur == 0) acc = 1;
+  emu::block_barrier();
+  if (!pred) acc = 0;
+  emu::block_barrier();
+  return acc;
+}
+inline void __nanosleep(unsigned) {}
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 template <typename T> inline T __ldg(const T* p) { return *p; }

@@ -24,26 +24,37 @@ def test_small_front_path(ctor, oracle_cls, ordering, monkeypatch):
     ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 40, 50, 12, ordering=ordering)
 
 
+@pytest.mark.parametrize("dag", ["1", "0"])
 @pytest.mark.parametrize("ordering", [0, 1])
-def test_tiled_front_path(ctor, oracle_cls, ordering, monkeypatch):
+def test_tiled_front_path(ctor, oracle_cls, ordering, monkeypatch, dag):
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")     # force every front of order > 8 onto the tiled path
+    monkeypatch.setenv("B2_DAG", dag)             # dataflow kernel (k_front_dag) / k_trsm + k_update launch chain
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
     N, r, c, v = random_kkt(50, 60, 15, 0.3, 22)
     B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 50, 60, 15, ordering=ordering)
     assert B.stats()["n_large"] > 0
 
 
-def test_tiled_path_multi_block_front(ctor, oracle_cls, monkeypatch):
-    """One dense front of order 150 on the tiled path: three pivot blocks (64, 64, 22), DMMA tiles."""
+@pytest.mark.parametrize("dag", ["1", "0"])
+def test_tiled_path_multi_block_front(ctor, oracle_cls, monkeypatch, dag):
+    """One dense front of order 150 on the tiled path: three pivot blocks (64, 64, 22), DMMA tiles;
+    with the dataflow kernel: a plain diagonal task, two chain tasks and one ypre task."""
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")
+    monkeypatch.setenv("B2_DAG", dag)
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
     N, r, c, v = random_kkt(60, 70, 20, 0.5, 71)
     B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 60, 70, 20, ordering=1)
     assert B.stats()["max_width"] > 128
 
 
-def test_tiled_path_multi_chunk_trsm(ctor, oracle_cls, monkeypatch):
+@pytest.mark.parametrize("dag", ["1", "0"])
+def test_tiled_path_multi_chunk_trsm(ctor, oracle_cls, monkeypatch, dag):
     """Order-260 dense front: the rows below the first pivot block span two k_trsm CTAs, so the
-    factored diagonal block must come from the staging area, not from the panel being read."""
+    factored diagonal block must come from the staging area, not from the panel being read
+    (launch chain); five row blocks with a contribution block (dataflow kernel)."""
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")
+    monkeypatch.setenv("B2_DAG", dag)
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
     N, r, c, v = random_kkt(100, 130, 30, 0.5, 73)
     ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 100, 130, 30, ordering=1)
 
@@ -75,6 +86,7 @@ def test_lookahead_diagonal_factorization_path(ctor, oracle_cls, monkeypatch):
     """The optional look-ahead schedule (k_diag on a side stream, prefactored k_trsm, k_update that
     leaves the next diagonal block alone) gives the same factorization."""
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")
+    monkeypatch.setenv("B2_DAG", "0")
     monkeypatch.setenv("B2_LOOKAHEAD", "1")
     N, r, c, v = random_kkt(60, 70, 20, 0.5, 71)
     ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 60, 70, 20, ordering=1)

@@ -33,14 +33,18 @@ def test_golden_vectors(ctor):
 
 @pytest.mark.parametrize("ordering", [0, 1, 3])
 @pytest.mark.parametrize("seed", [31, 32])
-def test_random_kkt_against_oracle(ctor, oracle_cls, ordering, seed):
+def test_random_kkt_against_oracle(ctor, oracle_cls, ordering, seed, monkeypatch):
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")     # every tiled front through k_front_dag, one-block fronts too
     nv, ne, nc = 300, 400, 80
     N, r, c, v = random_kkt(nv, ne, nc, 0.02, seed)
     ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=ordering)
 
 
-def test_dense_front_tiled_path_against_oracle(ctor, oracle_cls):
-    """One dense 700-order front: five+ pivot blocks, 11 x 11 update tiles."""
+@pytest.mark.parametrize("dag", ["1", "0"])
+def test_dense_front_tiled_path_against_oracle(ctor, oracle_cls, monkeypatch, dag):
+    """One dense 700-order front: five+ pivot blocks, 11 x 11 tiles; through the dataflow kernel
+    (k_front_dag: chain / ypre / plain tile tasks) and through the k_trsm / k_update launch chain."""
+    monkeypatch.setenv("B2_DAG", dag)
     nv, ne, nc = 250, 350, 100
     N, r, c, v = random_kkt(nv, ne, nc, 0.6, 33)
     B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=1)
