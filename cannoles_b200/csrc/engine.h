@@ -59,6 +59,7 @@ struct Engine {
   // k_trsm / k_update launch pair per 64-column pivot block); B2_DAG=0 selects the launch chain
   bool use_dag = true;
   int dag_min_np = 4;          // ... on the tree levels whose widest front has at least this many pivot blocks (B2_DAG_MIN_NP)
+  int dag_excl_max = 0;        // k_front_dag launches with at most this many tasks run one CTA per SM (B2_DAG_EXCL_MAX)
   int dag_ctas = 0;            // CTAs of a k_front_dag launch (resident CTAs of the device)
   int64_t ntflag = 0;          // tile flags of all tiled fronts; the ticket counters of the launches follow them
   int ndag = 0;

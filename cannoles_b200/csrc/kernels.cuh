@@ -721,21 +721,24 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
   const double* pa = Lp + gi + (size_t)k0 * m;
   const double* pb = Lp + gj + (size_t)k0 * m;
   const double* dv = P.dvec + c0 + k0;
-  double ra[KC / 4], rb[KC / 4];
+  double ra[KC / 4], rb[KC / 4], rk[KC / 4];
   const int nchunk = (K + KC - 1) / KC;
+  // the loads only: the product with d_k is formed when the registers go to shared memory, one
+  // chunk of tensor work later (a multiply here would wait for the loads it is meant to hide)
   auto gload = [&](int kc) {
     B2_UNROLL
     for (int p = 0; p < KC / 4; p++) {
       const int k = kc + lk + 4 * p;
       ra[p] = (vi && k < K) ? pa[(size_t)k * m] : 0.0;
-      rb[p] = (vj && k < K) ? pb[(size_t)k * m] * dv[k] : 0.0;
+      rb[p] = (vj && k < K) ? pb[(size_t)k * m] : 0.0;
+      rk[p] = (k < K) ? dv[k] : 0.0;
     }
   };
   auto sstore = [&](int buf) {
     B2_UNROLL
     for (int p = 0; p < KC / 4; p++) {
       As[buf][lk + 4 * p][lr] = ra[p];
-      Bs[buf][lk + 4 * p][lr] = rb[p];
+      Bs[buf][lk + 4 * p][lr] = rb[p] * rk[p];
     }
   };
   B2_TICK(20);
@@ -830,6 +833,7 @@ __device__ __forceinline__ long long dag_now() { long long v; asm volatile("mov.
 constexpr int DAG_LDT = TILE + 4;
 constexpr int DAG_LDL = NB + 1;
 constexpr int DAG_SMEM = (4 * UPD_KC * DAG_LDT + NB * DAG_LDT + NB * DAG_LDL + 8 * 64 + NB) * (int)sizeof(double);
+constexpr int DAG_SMEM_EXCL = 120 * 1024;   // more than half an SM's shared memory: one CTA per SM
 
 __device__ __forceinline__ int dag_peek(const int* f) {
 #ifdef B2_EMULATE
@@ -952,20 +956,22 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
         const double* pa = Lp + gi;
         const double* pb = Lp + gj;
         const double* dv = P.dvec + c0;
-        double ra[KC / 4], rb[KC / 4];
+        double ra[KC / 4], rb[KC / 4], rk[KC / 4];
+        // the loads only: the product with d_k is formed when the registers go to shared memory
         auto gload = [&](int kc) {
           B2_UNROLL
           for (int p = 0; p < KC / 4; p++) {
             const int k = kc + lk + 4 * p;
             ra[p] = (vi && k < Ktot) ? dag_ld(pa + (size_t)k * m) : 0.0;
-            rb[p] = (vj && k < Ktot) ? dag_ld(pb + (size_t)k * m) * dag_ld(dv + k) : 0.0;
+            rb[p] = (vj && k < Ktot) ? dag_ld(pb + (size_t)k * m) : 0.0;
+            rk[p] = (k < Ktot) ? dag_ld(dv + k) : 0.0;
           }
         };
         auto sstore = [&](int buf) {
           B2_UNROLL
           for (int p = 0; p < KC / 4; p++) {
             As[(buf * KC + lk + 4 * p) * LDT + lr] = ra[p];
-            Bs[(buf * KC + lk + 4 * p) * LDT + lr] = rb[p];
+            Bs[(buf * KC + lk + 4 * p) * LDT + lr] = rb[p] * rk[p];
           }
         };
         if (tid == 0) { dag_wait(fI); dag_wait(fJ); }
