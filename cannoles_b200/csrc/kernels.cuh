@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
         }
 #pragma unroll 4
         for (int i = ia + lane; i < iz; i += 32) dst[relc[i]] += src[i];
+        __syncwarp();   // the next (child, column) pair may land on the same rows through other lanes
       }
     }
   }

@@ -14,7 +14,10 @@ from cannoles_b200.linsolve import B200Struct  # noqa: E402
 from cannoles_b200.workloads import dense_batch_systems, first_system, make_config  # noqa: E402
 
 EPS = 2.0 ** -52
-for cfg, size in (("c4", 14), ("c2", 300)):
+# the last case has fronts with three pivot blocks and runs every tiled front through the dataflow
+# kernel (k_front_dag: plain, chain and ypre tasks); the first two take the k_trsm / k_update chain
+for cfg, size, dag_min_np in (("c4", 14, "99"), ("c2", 300, "99"), ("c4", 60, "1")):
+    os.environ["B2_DAG_MIN_NP"] = dag_min_np
     nls, method, _ = make_config(cfg, size)
     ctor = functools.partial(B200Struct, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon, refine_steps=1,
                              refine_tol=0.0, shift_retries=True)
@@ -26,7 +29,7 @@ for cfg, size in (("c4", 14), ("c2", 300)):
     d = np.zeros(B.N)
     B.solve_ldl(rhs, d)
     st = B.stats()
-    print(cfg, size, "N", B.N, "ok", ok, ok2, "relres", B.last_relres, "n_large", st["n_large"], "max_front", st["max_front"])
+    print(cfg, size, "N", B.N, "ok", ok, ok2, "relres", B.last_relres, "n_large", st["n_large"], "max_front", st["max_front"], "max_width", st["max_width"], "dag_min_np", dag_min_np)
     B.close()
 nb = 3
 s, vals, rhs = dense_batch_systems(range(nb))
