@@ -23,6 +23,7 @@ using std::max;
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
@@ -204,6 +205,15 @@ inline int __syncthreads_and(int pred) {
   if (emu::S().cur == 0) acc = 1;
   emu::block_barrier();
   if (!pred) acc = 0;
+  emu::block_barrier();
+  return acc;
+}
+inline int __syncthreads_or(int pred) {
+  static int acc;
+  emu::block_barrier();
+  if (emu::S().cur == 0) acc = 0;
+  emu::block_barrier();
+  if (pred) acc = 1;
   emu::block_barrier();
   return acc;
 }
