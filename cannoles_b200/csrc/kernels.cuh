@@ -1116,36 +1116,35 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
       __syncthreads();
       DAG_TRACE(5);
       {
+        // warp <-> 8 rows; left-looking over the 8-column blocks with ROLLED loops (this code runs
+        // once per task, cold: a fully unrolled right-looking version was instruction-fetch bound).
+        // W of the finished blocks sits in Ws (= As|Bs, [col][row]); two accumulator pairs halve
+        // the dependent DMMA chain.
+        double* Ws = As;
         const int row = warp * 8 + g;
-        double cf[8][2];
-        B2_UNROLL
-        for (int kb = 0; kb < 8; kb++) {
-          cf[kb][0] = T[(kb * 8 + 2 * t) * LDT + row];
-          cf[kb][1] = T[(kb * 8 + 2 * t + 1) * LDT + row];
-        }
-        __syncwarp();                            // T rows of this warp are rewritten below (chain)
         const int gi = i0 + row;
-        B2_UNROLL
         for (int kb = 0; kb < 8; kb++) {
-          const double a0 = frag_c2a(cf[kb][0], cf[kb][1], 0, lane), a1 = frag_c2a(cf[kb][0], cf[kb][1], 1, lane);
+          double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
+          const double* lrow = Lr + (kb * 8 + g) * LDL + t;
+          for (int tb = 0; tb < kb; tb++) {
+            dmma_8x8x4(s0, s1, Ws[(tb * 8 + t) * LDT + row], lrow[tb * 8]);
+            dmma_8x8x4(u0, u1, Ws[(tb * 8 + 4 + t) * LDT + row], lrow[tb * 8 + 4]);
+          }
+          const double c0v = T[(kb * 8 + 2 * t) * LDT + row] - (s0 + u0);
+          const double c1v = T[(kb * 8 + 2 * t + 1) * LDT + row] - (s1 + u1);
+          const double a0 = frag_c2a(c0v, c1v, 0, lane), a1 = frag_c2a(c0v, c1v, 1, lane);
           double w0 = 0.0, w1 = 0.0;
           dmma_8x8x4(w0, w1, a0, Mi[kb * 64 + g * 8 + t]);
           dmma_8x8x4(w0, w1, a1, Mi[kb * 64 + g * 8 + 4 + t]);
-          if (kb < 7) {
-            const double n0 = -frag_c2a(w0, w1, 0, lane), n1 = -frag_c2a(w0, w1, 1, lane);
-            B2_UNROLL
-            for (int k2 = kb + 1; k2 < 8; k2++) {
-              dmma_8x8x4(cf[k2][0], cf[k2][1], n0, Lr[(k2 * 8 + g) * LDL + kb * 8 + t]);
-              dmma_8x8x4(cf[k2][0], cf[k2][1], n1, Lr[(k2 * 8 + g) * LDL + kb * 8 + 4 + t]);
-            }
-          }
           B2_UNROLL
           for (int e = 0; e < 2; e++) {
             const int lc = kb * 8 + 2 * t + e;
             const double wv = e ? w1 : w0, lv = wv * rdv[lc];
             if (gi < iend && lc < nbs) Lp[gi + (size_t)(js0 + lc) * m] = lv;
-            if (chain) { As[lc * LDT + row] = wv; T[lc * LDT + row] = lv; }
+            Ws[lc * LDT + row] = wv;
+            if (chain) T[lc * LDT + row] = lv;
           }
+          __syncwarp();                          // W of block kb is read back as A fragments by the other lanes
         }
       }
       __syncthreads();
