@@ -46,8 +46,8 @@ METRIC = "kkt_factor_solve_per_s"
 UNIT = "KKT factor+solve/s"
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE factorization (all its kernels), from the ncu
-# capture summarised in profiles/traffic_r01_s.txt; only valid for the default workload
-KNOWN_TRAFFIC = {("c4", None, "nd"): 2352.7e6}
+# capture summarised in profiles/traffic_r01_u.txt; only valid for the default workload
+KNOWN_TRAFFIC = {("c4", None, "nd"): 2044.7e6}
 
 
 # ------------------------------------------------------------------------------------------
@@ -324,7 +324,7 @@ def run_b200(args):
             "bound": "tensor", "achieved": fact_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": (fact_tflops / fp64_peak) if fp64_peak else None,
             "traffic": KNOWN_TRAFFIC.get((args.workload, args.size, args.ordering)),
-            "traffic_note": "bytes per factorization, ncu cold-cache sum over its kernels (profiles/traffic_r01_s.txt); algorithmic bytes 8 (nnzA + nnzL + N)",
+            "traffic_note": "bytes per factorization, ncu cold-cache sum over its kernels (profiles/traffic_r01_u.txt); algorithmic bytes 8 (nnzA + nnzL + N)",
             "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
             "algorithmic_flops_per_launch": st["flops"], "ms_per_launch": ph[1],
             "hbm_view": {"achieved": bytes_fact / (ph[1] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
