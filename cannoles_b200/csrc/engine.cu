@@ -376,6 +376,62 @@ int Engine::build_plan() {
   if ((int64_t)asm_cptr.size() >= (int64_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "too many tiled-front columns"); return -1; }
   if (upload(&d_asm_off, asm_off, bytes_device)) return -1;
   plan.asm_cptr = d_asm_cptr; plan.asm_ent = d_asm_ent; plan.asm_rc = d_asm_rc; plan.asm_off = d_asm_off;
+  {
+    // forward solve of the fronts that are not "big": per front row, the child update entries that
+    // land on it, children ascending = the order the per-child loop added them in (bit-identical
+    // sums).  One pass replaces, per child, a chain of dependent loads (child -> scol / rptr / uptr ->
+    // rel -> upd) and a barrier: the gather of a front is now two load latencies whatever its
+    // number of children.
+    const int64_t nrows = S.rptr[S.nsuper];
+    if (nrows >= (int64_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "front row storage exceeds int32 offsets"); return -1; }
+    std::vector<int32_t> ug_ptr((size_t)nrows + 1, 0), ug_src;
+    std::vector<int32_t> cnt;
+    for (int s = 0; s < S.nsuper; s++) {
+      const int m = front_m(s);
+      const int64_t r0 = S.rptr[s];
+      if (m > (int)solve_big_m) continue;      // k_fwd_big has its own gather (sb_ptr / sb_src)
+      for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
+        const int c = S.child_idx[q];
+        const int wc = front_w(c), rc = front_m(c) - wc;
+        const int32_t* relc = &S.rel[S.rptr[c] + wc];
+        for (int k = 0; k < rc; k++) ug_ptr[r0 + relc[k] + 1]++;
+      }
+    }
+    for (int64_t i = 0; i < nrows; i++) ug_ptr[i + 1] += ug_ptr[i];
+    ug_src.resize((size_t)ug_ptr[nrows]);
+    for (int s = 0; s < S.nsuper; s++) {
+      const int m = front_m(s);
+      const int64_t r0 = S.rptr[s];
+      if (m > (int)solve_big_m) continue;
+      cnt.assign(m, 0);
+      for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
+        const int c = S.child_idx[q];
+        const int wc = front_w(c), rc = front_m(c) - wc;
+        const int32_t* relc = &S.rel[S.rptr[c] + wc];
+        for (int k = 0; k < rc; k++) ug_src[(size_t)ug_ptr[r0 + relc[k]] + cnt[relc[k]]++] = (int32_t)(S.uptr[c] + k);
+      }
+    }
+    if (upload(&d_ug_ptr, ug_ptr, bytes_device)) return -1;
+    if (upload(&d_ug_src, ug_src, bytes_device)) return -1;
+    plan.ug_ptr = d_ug_ptr; plan.ug_src = d_ug_src;
+  }
+  {
+    // one descriptor per child link, in child_idx order: the extend-add of a small front fetches the
+    // descriptors of 32 children at once instead of chasing child -> scol / rptr / cbptr per child
+    const size_t nlink = S.child_idx.size();
+    std::vector<int32_t> cd_rc(nlink);
+    std::vector<int64_t> cd_off(2 * nlink);
+    for (size_t q = 0; q < nlink; q++) {
+      const int c = S.child_idx[q];
+      const int wc = front_w(c);
+      cd_rc[q] = front_m(c) - wc;
+      cd_off[2 * q] = S.rptr[c] + wc;
+      cd_off[2 * q + 1] = S.cbptr[c];
+    }
+    if (upload(&d_cd_rc, cd_rc, bytes_device)) return -1;
+    if (upload(&d_cd_off, cd_off, bytes_device)) return -1;
+    plan.cd_rc = d_cd_rc; plan.cd_off = d_cd_off;
+  }
   if (upload(&d_sb_ptr, sb_ptr, bytes_device)) return -1;
   if (upload(&d_sb_src, sb_src, bytes_device)) return -1;
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
@@ -477,7 +533,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ypub, d_tflag, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_cd_rc, d_cd_off, d_ypub, d_tflag, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);

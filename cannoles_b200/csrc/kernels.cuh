@@ -95,18 +95,53 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
   for (int64_t q = P.amap_ptr[s] + tid; q < P.amap_ptr[s + 1]; q += NT)
     F[P.amap_pos[q]] = P.nzval[P.amap_slot[q]];
   B2_FSYNC();
-  for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
-    const int c = P.child_idx[ci];
-    const int wc = P.scol[c + 1] - P.scol[c];
-    const int64_t rc0 = P.rptr[c] + wc;
-    const int rc = (int)(P.rptr[c + 1] - rc0);
-    const int32_t* relc = P.rel + rc0;
-    const double* cb = P.CB + P.cbptr[c];
-    for (int j = warp; j < rc; j += NW) {
-      const int J = relc[j];
-      for (int i = j + lane; i < rc; i += 32) F[relc[i] + J * m] += cb[i + (size_t)j * rc];
+  // extend-add, children ascending (deterministic sums).  The lanes fetch the descriptors of 32
+  // children at once (host-built, one per child link); per child every warp takes four columns of
+  // the contribution block per round and issues all their loads before the first add: the loop is
+  // bound by the number of dependent global round trips, not by bandwidth.
+  {
+    const int ci0 = P.child_ptr[s], ci1 = P.child_ptr[s + 1];
+    for (int cb0 = ci0; cb0 < ci1; cb0 += 32) {
+      const int cnt = min(32, ci1 - cb0);
+      int rcv = 0;
+      long long ro = 0, co = 0;
+      if (lane < cnt) {
+        rcv = P.cd_rc[cb0 + lane];
+        ro = P.cd_off[2 * (cb0 + lane)];
+        co = P.cd_off[2 * (cb0 + lane) + 1];
+      }
+      for (int k = 0; k < cnt; k++) {
+        const int rc = __shfl_sync(0xffffffffu, rcv, k);
+        const int32_t* relc = P.rel + __shfl_sync(0xffffffffu, ro, k);
+        const double* cb = P.CB + __shfl_sync(0xffffffffu, co, k);
+        for (int j0 = warp * 4; j0 < rc; j0 += NW * 4) {
+          int ri[4], Jv[4];
+          double v[4][4];
+          B2_UNROLL
+          for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; ri[q] = (i < rc) ? relc[i] : 0; }
+          B2_UNROLL
+          for (int u = 0; u < 4; u++) {
+            const int j = j0 + u;
+            Jv[u] = (j < rc) ? relc[j] : 0;
+            B2_UNROLL
+            for (int q = 0; q < 4; q++) {
+              const int i = lane + 32 * q;
+              v[u][q] = (j < rc && i >= j && i < rc) ? cb[i + (size_t)j * rc] : 0.0;
+            }
+          }
+          B2_UNROLL
+          for (int u = 0; u < 4; u++) {
+            const int j = j0 + u;
+            B2_UNROLL
+            for (int q = 0; q < 4; q++) {
+              const int i = lane + 32 * q;
+              if (j < rc && i >= j && i < rc) F[ri[q] + Jv[u] * m] += v[u][q];
+            }
+          }
+        }
+        B2_FSYNC();
+      }
     }
-    B2_FSYNC();
   }
   // eliminate the w pivot columns: rank-1 updates restricted to the pivot columns ...
   for (int k = 0; k < w; k++) {
@@ -1272,18 +1307,20 @@ __global__ void __launch_bounds__(NT * FPB) k_fwd(PlanDev P, const int32_t* __re
   const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
   const int tid = (FPB > 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* Lp = P.Lx + P.lptr[s];
-  for (int i = tid; i < m; i += NT) xs[i] = (i < w) ? x[c0 + i] : 0.0;
-  B2_FSYNC();
-  for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
-    const int c = P.child_idx[ci];
-    const int wc = P.scol[c + 1] - P.scol[c];
-    const int64_t rc0 = P.rptr[c] + wc;
-    const int rc = (int)(P.rptr[c + 1] - rc0);
-    const int32_t* relc = P.rel + rc0;
-    const double* uc = upd + P.uptr[c];
-    for (int k = tid; k < rc; k += NT) xs[relc[k]] += uc[k];
-    B2_FSYNC();
+  // own entries of the right-hand side + the children's update vectors: a per-row gather built on
+  // the host (ug_ptr / ug_src, children ascending => the sums of the per-child loop, bit for bit),
+  // one thread per row, independent loads, no barrier per child
+  {
+    const int32_t* gp = P.ug_ptr + P.rptr[s];
+    for (int i = tid; i < m; i += NT) {
+      double acc = (i < w) ? x[c0 + i] : 0.0;
+      const int e1 = gp[i + 1];
+#pragma unroll 4
+      for (int e = gp[i]; e < e1; e++) acc += upd[P.ug_src[e]];
+      xs[i] = acc;
+    }
   }
+  B2_FSYNC();
   for (int jb = 0; jb < w; jb += SNB) {
     const int nb = min(SNB, w - jb);
     if (warp == 0) {
@@ -1381,15 +1418,14 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_fwd_tiny(PlanDev P, const int32
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
   const double* Lp = P.Lx + P.lptr[s];
-  for (int i = 0; i < m; i++) xs[i * TNT] = (i < w) ? x[c0 + i] : 0.0;
-  for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
-    const int c = P.child_idx[ci];
-    const int wc = P.scol[c + 1] - P.scol[c];
-    const int64_t rc0 = P.rptr[c] + wc;
-    const int rc = (int)(P.rptr[c + 1] - rc0);
-    const int32_t* relc = P.rel + rc0;
-    const double* uc = upd + P.uptr[c];
-    for (int k = 0; k < rc; k++) xs[relc[k] * TNT] += uc[k];
+  {
+    const int32_t* gp = P.ug_ptr + P.rptr[s];
+    for (int i = 0; i < m; i++) {
+      double acc = (i < w) ? x[c0 + i] : 0.0;
+      const int e1 = gp[i + 1];
+      for (int e = gp[i]; e < e1; e++) acc += upd[P.ug_src[e]];
+      xs[i * TNT] = acc;
+    }
   }
   for (int j = 0; j < w; j++) {
     const double yj = xs[j * TNT];

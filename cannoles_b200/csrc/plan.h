@@ -30,6 +30,10 @@ struct PlanDev {
   const int64_t* sb_ptr;   // big-front solve: per (chunk, row) CSR pointers into sb_src (SB + 1 per chunk)
   const int32_t* sb_src;   // offsets into the update-vector storage, in child order
   const int32_t* sb_flag;  // per front: offset of its block flags (big fronts only)
+  const int32_t* ug_ptr;   // forward solve of the other fronts: per front row (rptr[s] + i) the range in ug_src
+  const int32_t* ug_src;   //   of the child update entries (offsets into upd) that land on it, in child order
+  const int32_t* cd_rc;    // per child link (position in child_idx): order of the child's contribution block
+  const int64_t* cd_off;   //   and the offsets of its rel[] rows and of its contribution block (pairs)
   int* flags;  // [0] = breakdown (exact zero pivot seen)
 };
 
