@@ -143,30 +143,26 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
       }
     }
   }
-  // eliminate the w pivot columns: rank-1 updates restricted to the pivot columns ...
+  // eliminate the w pivot columns: rank-1 updates restricted to the pivot columns, ONE barrier per
+  // pivot.  The pivot columns stay unscaled (A = L D) until the end: the update of column j by
+  // pivot k is F(i,j) -= F(i,k) * (F(j,k) / d_k), every warp forms the multiplier of its own
+  // columns, nothing is staged in between; lk keeps 1 / d_k.
   for (int k = 0; k < w; k++) {
     const double dk = F[k + k * m];
     const double rdk = rcp_nr(dk);
-    for (int i = k + 1 + tid; i < m; i += NT) {
-      const double a = F[i + k * m];
-      const double l = a * rdk;
-      ak[i] = a;
-      lk[i] = l;
-      F[i + k * m] = l;
-    }
     if (tid == 0) {
+      lk[k] = rdk;
       P.dvec[c0 + k] = dk;
       if (dk == 0.0) P.flags[0] = 1;
     }
-    B2_FSYNC();
     for (int j = k + 1 + warp; j < w; j += NW) {
-      const double ajk = ak[j];
-      for (int i = j + lane; i < m; i += 32) F[i + j * m] -= lk[i] * ajk;
+      const double tjk = F[j + k * m] * rdk;
+      for (int i = j + lane; i < m; i += 32) F[i + j * m] -= F[i + k * m] * tjk;
     }
     B2_FSYNC();
   }
   // ... then ONE rank-w update of the contribution block, C -= L21 D L21^T, in 8 x 8 x 4 FP64
-  // tensor-core tiles straight from shared memory (d_k sits on the diagonal of the panel)
+  // tensor-core tiles straight from shared memory (A = L D is what the panel still holds)
   if (r > 0) {
     const int nt8 = (r + 7) >> 3;
     const int g = lane >> 2, t = lane & 3;
@@ -179,8 +175,8 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
         const int k = k0 + t;
         double av = 0.0, bv = 0.0;
         if (k < w) {
-          if (ra < m) av = F[ra + k * m];
-          if (rb < m) bv = F[rb + k * m] * F[k + k * m];
+          if (ra < m) av = F[ra + k * m] * lk[k];
+          if (rb < m) bv = F[rb + k * m];
         }
         dmma_8x8x4(acc0, acc1, av, bv);
       }
@@ -192,8 +188,12 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
     }
     B2_FSYNC();
   }
+  // panel: strict lower part scaled to L on the way out, D on the diagonal
   double* Lp = P.Lx + P.lptr[s];
-  for (int idx = tid; idx < m * w; idx += NT) Lp[idx] = F[idx];
+  for (int idx = tid; idx < m * w; idx += NT) {
+    const int kk = idx / m, i = idx - kk * m;
+    Lp[idx] = (i > kk) ? F[idx] * lk[kk] : F[idx];
+  }
   double* cbp = P.CB + P.cbptr[s];
   for (int j = warp; j < r; j += NW)
     for (int i = j + lane; i < r; i += 32) cbp[i + (size_t)j * r] = F[(w + i) + (w + j) * m];
