@@ -399,6 +399,7 @@ int Engine::build_plan() {
     }
     for (int64_t i = 0; i < nrows; i++) ug_ptr[i + 1] += ug_ptr[i];
     ug_src.resize((size_t)ug_ptr[nrows]);
+    std::vector<uint8_t> ug_row(ug_src.size() + 1, 0);
     for (int s = 0; s < S.nsuper; s++) {
       const int m = front_m(s);
       const int64_t r0 = S.rptr[s];
@@ -408,12 +409,17 @@ int Engine::build_plan() {
         const int c = S.child_idx[q];
         const int wc = front_w(c), rc = front_m(c) - wc;
         const int32_t* relc = &S.rel[S.rptr[c] + wc];
-        for (int k = 0; k < rc; k++) ug_src[(size_t)ug_ptr[r0 + relc[k]] + cnt[relc[k]]++] = (int32_t)(S.uptr[c] + k);
+        for (int k = 0; k < rc; k++) {
+          const size_t e = (size_t)ug_ptr[r0 + relc[k]] + cnt[relc[k]]++;
+          ug_src[e] = (int32_t)(S.uptr[c] + k);
+          ug_row[e] = (uint8_t)std::min(relc[k], 255);
+        }
       }
     }
     if (upload(&d_ug_ptr, ug_ptr, bytes_device)) return -1;
     if (upload(&d_ug_src, ug_src, bytes_device)) return -1;
-    plan.ug_ptr = d_ug_ptr; plan.ug_src = d_ug_src;
+    if (upload(&d_ug_row, ug_row, bytes_device)) return -1;
+    plan.ug_ptr = d_ug_ptr; plan.ug_src = d_ug_src; plan.ug_row = d_ug_row;
   }
   {
     // one descriptor per child link, in child_idx order: the extend-add of a small front fetches the
@@ -533,7 +539,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_cd_rc, d_cd_off, d_ypub, d_tflag, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_cd_rc, d_cd_off, d_ypub, d_tflag, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);

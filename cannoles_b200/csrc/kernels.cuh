@@ -1418,14 +1418,14 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_fwd_tiny(PlanDev P, const int32
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
   const double* Lp = P.Lx + P.lptr[s];
+  // the children's update entries of a front are contiguous in ug_src (row by row, children
+  // ascending within a row): one flat loop whose loads are independent of each other
+  for (int i = 0; i < m; i++) xs[i * TNT] = (i < w) ? x[c0 + i] : 0.0;
   {
     const int32_t* gp = P.ug_ptr + P.rptr[s];
-    for (int i = 0; i < m; i++) {
-      double acc = (i < w) ? x[c0 + i] : 0.0;
-      const int e1 = gp[i + 1];
-      for (int e = gp[i]; e < e1; e++) acc += upd[P.ug_src[e]];
-      xs[i * TNT] = acc;
-    }
+    const int e1 = gp[m];
+#pragma unroll 4
+    for (int e = gp[0]; e < e1; e++) xs[P.ug_row[e] * TNT] += upd[P.ug_src[e]];
   }
   for (int j = 0; j < w; j++) {
     const double yj = xs[j * TNT];
