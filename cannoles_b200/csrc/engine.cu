@@ -421,23 +421,6 @@ int Engine::build_plan() {
     if (upload(&d_ug_row, ug_row, bytes_device)) return -1;
     plan.ug_ptr = d_ug_ptr; plan.ug_src = d_ug_src; plan.ug_row = d_ug_row;
   }
-  {
-    // one descriptor per child link, in child_idx order: the extend-add of a small front fetches the
-    // descriptors of 32 children at once instead of chasing child -> scol / rptr / cbptr per child
-    const size_t nlink = S.child_idx.size();
-    std::vector<int32_t> cd_rc(nlink);
-    std::vector<int64_t> cd_off(2 * nlink);
-    for (size_t q = 0; q < nlink; q++) {
-      const int c = S.child_idx[q];
-      const int wc = front_w(c);
-      cd_rc[q] = front_m(c) - wc;
-      cd_off[2 * q] = S.rptr[c] + wc;
-      cd_off[2 * q + 1] = S.cbptr[c];
-    }
-    if (upload(&d_cd_rc, cd_rc, bytes_device)) return -1;
-    if (upload(&d_cd_off, cd_off, bytes_device)) return -1;
-    plan.cd_rc = d_cd_rc; plan.cd_off = d_cd_off;
-  }
   if (upload(&d_sb_ptr, sb_ptr, bytes_device)) return -1;
   if (upload(&d_sb_src, sb_src, bytes_device)) return -1;
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
@@ -539,7 +522,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_cd_rc, d_cd_off, d_ypub, d_tflag, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);

@@ -82,8 +82,6 @@ struct Engine {
   double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr, *d_dstage = nullptr;
   int64_t *d_dsptr = nullptr, *d_asm_cptr = nullptr, *d_asm_off = nullptr, *d_sb_ptr = nullptr;
   int32_t *d_asm_ent = nullptr, *d_asm_rc = nullptr, *d_sb_src = nullptr, *d_sb_flag = nullptr;
-  int32_t* d_cd_rc = nullptr;   // per child link descriptors (k_front_small)
-  int64_t* d_cd_off = nullptr;
   uint8_t* d_ug_row = nullptr;
   int32_t *d_ug_ptr = nullptr, *d_ug_src = nullptr;   // per-row gather of the children's update vectors (k_fwd, k_fwd_tiny)
   int64_t nsflag = 0;          // pivot blocks of the big fronts (0: no multi-CTA solves)

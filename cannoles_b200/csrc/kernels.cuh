@@ -95,74 +95,43 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
   for (int64_t q = P.amap_ptr[s] + tid; q < P.amap_ptr[s + 1]; q += NT)
     F[P.amap_pos[q]] = P.nzval[P.amap_slot[q]];
   B2_FSYNC();
-  // extend-add, children ascending (deterministic sums).  The lanes fetch the descriptors of 32
-  // children at once (host-built, one per child link); per child every warp takes four columns of
-  // the contribution block per round and issues all their loads before the first add: the loop is
-  // bound by the number of dependent global round trips, not by bandwidth.
-  {
-    const int ci0 = P.child_ptr[s], ci1 = P.child_ptr[s + 1];
-    for (int cb0 = ci0; cb0 < ci1; cb0 += 32) {
-      const int cnt = min(32, ci1 - cb0);
-      int rcv = 0;
-      long long ro = 0, co = 0;
-      if (lane < cnt) {
-        rcv = P.cd_rc[cb0 + lane];
-        ro = P.cd_off[2 * (cb0 + lane)];
-        co = P.cd_off[2 * (cb0 + lane) + 1];
-      }
-      for (int k = 0; k < cnt; k++) {
-        const int rc = __shfl_sync(0xffffffffu, rcv, k);
-        const int32_t* relc = P.rel + __shfl_sync(0xffffffffu, ro, k);
-        const double* cb = P.CB + __shfl_sync(0xffffffffu, co, k);
-        for (int j0 = warp * 4; j0 < rc; j0 += NW * 4) {
-          int ri[4], Jv[4];
-          double v[4][4];
-          B2_UNROLL
-          for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; ri[q] = (i < rc) ? relc[i] : 0; }
-          B2_UNROLL
-          for (int u = 0; u < 4; u++) {
-            const int j = j0 + u;
-            Jv[u] = (j < rc) ? relc[j] : 0;
-            B2_UNROLL
-            for (int q = 0; q < 4; q++) {
-              const int i = lane + 32 * q;
-              v[u][q] = (j < rc && i >= j && i < rc) ? cb[i + (size_t)j * rc] : 0.0;
-            }
-          }
-          B2_UNROLL
-          for (int u = 0; u < 4; u++) {
-            const int j = j0 + u;
-            B2_UNROLL
-            for (int q = 0; q < 4; q++) {
-              const int i = lane + 32 * q;
-              if (j < rc && i >= j && i < rc) F[ri[q] + Jv[u] * m] += v[u][q];
-            }
-          }
-        }
-        B2_FSYNC();
-      }
+  for (int ci = P.child_ptr[s]; ci < P.child_ptr[s + 1]; ci++) {
+    const int c = P.child_idx[ci];
+    const int wc = P.scol[c + 1] - P.scol[c];
+    const int64_t rc0 = P.rptr[c] + wc;
+    const int rc = (int)(P.rptr[c + 1] - rc0);
+    const int32_t* relc = P.rel + rc0;
+    const double* cb = P.CB + P.cbptr[c];
+    for (int j = warp; j < rc; j += NW) {
+      const int J = relc[j];
+      for (int i = j + lane; i < rc; i += 32) F[relc[i] + J * m] += cb[i + (size_t)j * rc];
     }
+    B2_FSYNC();
   }
-  // eliminate the w pivot columns: rank-1 updates restricted to the pivot columns, ONE barrier per
-  // pivot.  The pivot columns stay unscaled (A = L D) until the end: the update of column j by
-  // pivot k is F(i,j) -= F(i,k) * (F(j,k) / d_k), every warp forms the multiplier of its own
-  // columns, nothing is staged in between; lk keeps 1 / d_k.
+  // eliminate the w pivot columns: rank-1 updates restricted to the pivot columns ...
   for (int k = 0; k < w; k++) {
     const double dk = F[k + k * m];
     const double rdk = rcp_nr(dk);
+    for (int i = k + 1 + tid; i < m; i += NT) {
+      const double a = F[i + k * m];
+      const double l = a * rdk;
+      ak[i] = a;
+      lk[i] = l;
+      F[i + k * m] = l;
+    }
     if (tid == 0) {
-      lk[k] = rdk;
       P.dvec[c0 + k] = dk;
       if (dk == 0.0) P.flags[0] = 1;
     }
+    B2_FSYNC();
     for (int j = k + 1 + warp; j < w; j += NW) {
-      const double tjk = F[j + k * m] * rdk;
-      for (int i = j + lane; i < m; i += 32) F[i + j * m] -= F[i + k * m] * tjk;
+      const double ajk = ak[j];
+      for (int i = j + lane; i < m; i += 32) F[i + j * m] -= lk[i] * ajk;
     }
     B2_FSYNC();
   }
   // ... then ONE rank-w update of the contribution block, C -= L21 D L21^T, in 8 x 8 x 4 FP64
-  // tensor-core tiles straight from shared memory (A = L D is what the panel still holds)
+  // tensor-core tiles straight from shared memory (d_k sits on the diagonal of the panel)
   if (r > 0) {
     const int nt8 = (r + 7) >> 3;
     const int g = lane >> 2, t = lane & 3;
@@ -175,8 +144,8 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
         const int k = k0 + t;
         double av = 0.0, bv = 0.0;
         if (k < w) {
-          if (ra < m) av = F[ra + k * m] * lk[k];
-          if (rb < m) bv = F[rb + k * m];
+          if (ra < m) av = F[ra + k * m];
+          if (rb < m) bv = F[rb + k * m] * F[k + k * m];
         }
         dmma_8x8x4(acc0, acc1, av, bv);
       }
@@ -188,12 +157,8 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
     }
     B2_FSYNC();
   }
-  // panel: strict lower part scaled to L on the way out, D on the diagonal
   double* Lp = P.Lx + P.lptr[s];
-  for (int idx = tid; idx < m * w; idx += NT) {
-    const int kk = idx / m, i = idx - kk * m;
-    Lp[idx] = (i > kk) ? F[idx] * lk[kk] : F[idx];
-  }
+  for (int idx = tid; idx < m * w; idx += NT) Lp[idx] = F[idx];
   double* cbp = P.CB + P.cbptr[s];
   for (int j = warp; j < r; j += NW)
     for (int i = j + lane; i < r; i += 32) cbp[i + (size_t)j * r] = F[(w + i) + (w + j) * m];

@@ -33,8 +33,6 @@ struct PlanDev {
   const int32_t* ug_ptr;   // forward solve of the other fronts: per front row (rptr[s] + i) the range in ug_src
   const int32_t* ug_src;   //   of the child update entries (offsets into upd) that land on it, in child order
   const uint8_t* ug_row;   //   and the row of the front each entry lands on (fronts of order <= 255: the thread-per-front kernels)
-  const int32_t* cd_rc;    // per child link (position in child_idx): order of the child's contribution block
-  const int64_t* cd_off;   //   and the offsets of its rel[] rows and of its contribution block (pairs)
   int* flags;  // [0] = breakdown (exact zero pivot seen)
 };
 
