@@ -426,7 +426,7 @@ int Engine::build_plan() {
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
   if (dalloc(&d_ypub, (size_t)(2 * S.N), bytes_device)) return -1;   // forward | backward publication slots
   plan.sb_ptr = d_sb_ptr; plan.sb_src = d_sb_src; plan.sb_flag = d_sb_flag;
-  if (dalloc(&d_tflag, (size_t)(ntflag + ndag + 256), bytes_device)) return -1;   // tile flags | ticket counters | per-SM priority counters
+  if (dalloc(&d_tflag, (size_t)(ntflag + ndag + 1), bytes_device)) return -1;   // tile flags | ticket counters
   std::reverse(bwd_launches.begin(), bwd_launches.end());
   if (upload(&d_items, items, bytes_device)) return -1;
   return 0;
@@ -567,10 +567,10 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       // FP64 pipe with a neighbour's update (measured: LDL^T of a 64 x 64 tile 16 -> 11.5 us)
       if (L.count <= dag_excl_max)
         B2_LAUNCH(k_front_dag, std::min(L.count, dag_ctas / 2), 256, DAG_SMEM_EXCL, st, plan, it, L.count, d_tflag,
-                  d_tflag + ntflag + L.jb, d_tflag + ntflag + ndag, L.mode);
+                  d_tflag + ntflag + L.jb, L.mode);
       else
         B2_LAUNCH(k_front_dag, std::min(L.count, dag_ctas), 256, DAG_SMEM, st, plan, it, L.count, d_tflag,
-                  d_tflag + ntflag + L.jb, d_tflag + ntflag + ndag, L.mode);
+                  d_tflag + ntflag + L.jb, L.mode);
       break;
     case LK_FWD:
       if (L.cls == 0) { auto kfn = k_fwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, st, plan, it, L.count, d_x, d_upd, L.smem); }
@@ -673,7 +673,7 @@ int Engine::run_list(const std::vector<Launch>& LL, bool allow_fork) {
 
 int Engine::run_factor_launches() {
   // tile flags and ticket counters of the dataflow launches
-  if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + ndag + 256) * sizeof(int), stream));
+  if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + ndag) * sizeof(int), stream));
   return run_list(fact_launches, true);
 }
 
@@ -710,7 +710,7 @@ int Engine::profile(int which, int max, int* kinds, int* cls, int* counts, doubl
   for (int rep = 0; rep < 2; rep++) {   // second pass is the warm one
     if (which == 0) {
       B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
-      if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + ndag + 256) * sizeof(int), stream));
+      if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + ndag) * sizeof(int), stream));
     } else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
     B2_CUDA_OK(cudaEventRecord(evs[0], stream));
     for (size_t i = 0; i < LL.size(); i++) {

@@ -873,15 +873,6 @@ __device__ __forceinline__ void dag_raise(int* f) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
 #endif
 }
-__device__ __forceinline__ int dag_smid() {
-#ifdef B2_EMULATE
-  return 0;
-#else
-  unsigned v;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
-  return (int)(v & 255u);
-#endif
-}
 // operands written by other CTAs of the same launch: read through L2
 __device__ __forceinline__ double dag_ld(const double* p) {
 #ifdef B2_EMULATE
@@ -898,7 +889,7 @@ __device__ __forceinline__ double frag_c2a(double c0, double c1, int h, int lane
 }
 
 __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* __restrict__ items, int ntasks,
-                                                      int* __restrict__ tflag, int* __restrict__ ticket, int* __restrict__ busy_sm, int trace_base) {
+                                                      int* __restrict__ tflag, int* __restrict__ ticket, int trace_base) {
   constexpr int KC = UPD_KC, LDT = DAG_LDT, LDL = DAG_LDL;
   B2_DYN_SMEM(raw);
   double* As = reinterpret_cast<double*>(raw);   // [2][KC][LDT]
@@ -912,12 +903,6 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp & 1, wc = warp >> 1;       // warp tile of the update: rows wr*32.., cols wc*16..
   const int lr = tid & 63, lk = tid >> 6;
-  // Priority for the pivot chain: a task that is factoring / substituting a diagonal tile (nothing
-  // else in the front can start before it is done) raises a per-SM counter, and the update loop of
-  // a CTA that shares the SM pauses while it is up -- otherwise the neighbour's DMMA stream owns
-  // the FP64 pipe and the chain's dependent DFMAs queue behind it (LDL^T of a tile: 16 vs 11.5 us).
-  // A task raises the counter only after its last wait, so nobody it pauses can be needed by it.
-  int* busy = busy_sm + dag_smid();
   for (;;) {
     __syncthreads();                             // the previous task is done with shared memory and s_tk
     if (tid == 0) s_tk = atomicAdd(ticket, 1);
@@ -1011,7 +996,6 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
           const int buf = c & 1;
           const bool more = c + 1 < nchunk;
           const int kn = (c + 1) * KC;
-          const int yield = dag_peek_relaxed(busy);   // consumed after the chunk: its latency is hidden
           bool pre = more;
           if (more && (kn % NB) == 0) {          // the next chunk starts a new pivot block: is it there yet?
             const int pn = kn / NB;
@@ -1040,10 +1024,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
             }
             sstore(buf ^ 1);
           }
-          if (__syncthreads_or(yield)) {         // a pivot chain is running on this SM: stand aside
-            if (tid == 0) while (dag_peek_relaxed(busy) != 0) __nanosleep(500);
-            __syncthreads();
-          }
+          __syncthreads();
         }
       }
       // from here on acc = -(updated tile): the original tile is folded in (frees its registers)
@@ -1104,7 +1085,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
       const int js0 = Js * NB, nbs = min(NB, w - js0);
       const double* stage = P.dstage + P.dsptr[s] + (size_t)Js * NB * NB;
       int* fS = tflag + fb + Js * nrb;           // flags of column Js
-      if (tid == 0) { dag_wait(fS + Js); if (chain) atomicAdd(busy, 1); }
+      if (tid == 0) dag_wait(fS + Js);
       __syncthreads();
       DAG_TRACE(4);
       for (int idx = tid; idx < NB * NB; idx += 256) {
@@ -1175,7 +1156,6 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
     {
       const int j0 = J * NB, nb = min(NB, w - j0);
       double* stage = P.dstage + P.dsptr[s] + (size_t)J * NB * NB;
-      if (!chain && tid == 0) atomicAdd(busy, 1);   // a chain task raised it before its substitution
       B2_UNROLL
       for (int a = 0; a < 4; a++)
         B2_UNROLL
@@ -1217,7 +1197,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
         stage[512 + c] = (c < nb) ? rcp_nr(T[c + c * DIAG_LD]) : 1.0;
       }
       __syncthreads();
-      if (tid == 0) { dag_raise(tflag + fb + J * nrb + J); atomicAdd(busy, -1); }
+      if (tid == 0) dag_raise(tflag + fb + J * nrb + J);
       DAG_TRACE(9);
     }
   }
