@@ -222,20 +222,16 @@ int Engine::build_plan() {
     // launches otherwise); levels made of thousands of one-block fronts are faster on the chain
     if (use_dag && level_np >= dag_min_np) {
       for (int s : large) front_dag[s] = 1;
-      // one task per NB x NB tile (I, J), I >= J, of every tiled front of the level; ticket order =
-      // column by column across the fronts (bigger fronts first), which is a topological order of
-      // the tile dependencies (see k_front_dag)
+      // tasks over the NB x NB tiles (I, J), I >= J, of every tiled front of the level (see k_front_dag)
       Launch G; G.kind = LK_DAG; G.off = (int64_t)items.size(); G.jb = ndag++;
       struct FG { int s, nrb; int32_t fb; int m; };
       std::vector<FG> fg;
-      int maxnrb = 0;
       for (int s : large) {
         int w = front_w(s), m = front_m(s);
         int np = (w + NB - 1) / NB, nrb = np + (m - w + NB - 1) / NB;
         if (ntflag + (int64_t)np * (nrb + 1) >= (int64_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "too many tiles"); return -1; }
         fg.push_back({s, nrb, (int32_t)ntflag, m});
         ntflag += (int64_t)np * (nrb + 1);   // one flag per tile of the pivot columns + one per ypre task
-        maxnrb = std::max(maxnrb, nrb);
       }
       std::stable_sort(fg.begin(), fg.end(), [](const FG& a, const FG& b) { return a.m > b.m; });
       // ticket order = waves of the tile DAG over all fronts of the level (a topological order):
