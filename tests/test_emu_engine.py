@@ -47,6 +47,21 @@ def test_tiled_path_multi_block_front(ctor, oracle_cls, monkeypatch, dag):
     assert B.stats()["max_width"] > 128
 
 
+@pytest.mark.parametrize("N", [64, 65, 127, 128, 129, 193])
+def test_dataflow_kernel_tile_boundaries(ctor, oracle_cls, monkeypatch, N):
+    """One dense root front of order N through k_front_dag: full and partial last pivot blocks (N a
+    multiple of 64, one more, one less), one to four pivot blocks (plain, chain and ypre tasks)."""
+    monkeypatch.setenv("B2_SMALL_MAX_M", "8")
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    nv = N // 3
+    ne = N // 2
+    nc = N - nv - ne
+    Nk, r, c, v = random_kkt(nv, ne, nc, 0.9, 100 + N)
+    assert Nk == N
+    B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=1)
+    assert B.stats()["max_width"] == N
+
+
 @pytest.mark.parametrize("dag", ["1", "0"])
 def test_tiled_path_multi_chunk_trsm(ctor, oracle_cls, monkeypatch, dag):
     """Order-260 dense front: the rows below the first pivot block span two k_trsm CTAs, so the

@@ -51,6 +51,20 @@ def test_dense_front_tiled_path_against_oracle(ctor, oracle_cls, monkeypatch, da
     assert B.stats()["n_large"] >= 1 and B.stats()["max_front"] >= 600
 
 
+@pytest.mark.parametrize("N", [64, 65, 127, 128, 129, 192, 193, 257, 320])
+def test_dataflow_kernel_tile_boundaries(ctor, oracle_cls, monkeypatch, N):
+    """One dense root front of order N through k_front_dag: full and partial last pivot blocks,
+    one to five pivot blocks (plain, chain and ypre tasks)."""
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    nv = N // 3
+    ne = N // 2
+    nc = N - nv - ne
+    Nk, r, c, v = random_kkt(nv, ne, nc, 0.9, 100 + N)
+    assert Nk == N
+    B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=1)
+    assert B.stats()["max_width"] == N
+
+
 def test_empty_blocks_and_tiny_systems(ctor, oracle_cls):
     """ncon = 0 (unconstrained: no delta segment) and a 1 x 1 system."""
     N, r, c, v = random_kkt(12, 20, 0, 0.3, 34)
