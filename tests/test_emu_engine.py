@@ -62,6 +62,20 @@ def test_dataflow_kernel_tile_boundaries(ctor, oracle_cls, monkeypatch, N):
     assert B.stats()["max_width"] == N
 
 
+def test_dataflow_kernel_zero_pivot_is_reported_and_does_not_hang(ctor, monkeypatch):
+    """An exact zero as the very first pivot of a 193-order front in k_front_dag: the breakdown flag
+    comes back, every tile flag is still raised (the tasks behind it run on NaNs instead of waiting)."""
+    monkeypatch.setenv("B2_SMALL_MAX_M", "8")
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    nv, ne, nc = 64, 96, 33
+    N, r, c, v = random_kkt(nv, ne, nc, 0.9, 293)
+    v = v.copy()
+    v[(r == 1) & (c == 1)] = 0.0
+    B = ctor(N, r, c, v, nvar=nv, nequ=ne, ncon=nc, ordering=1, refine_steps=0)
+    assert B.try_to_factorize(v, nv, ne, nc, EPS) is False
+    assert B.last_inertia[3] is True
+
+
 @pytest.mark.parametrize("dag", ["1", "0"])
 def test_tiled_path_multi_chunk_trsm(ctor, oracle_cls, monkeypatch, dag):
     """Order-260 dense front: the rows below the first pivot block span two k_trsm CTAs, so the

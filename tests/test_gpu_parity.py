@@ -65,6 +65,20 @@ def test_dataflow_kernel_tile_boundaries(ctor, oracle_cls, monkeypatch, N):
     assert B.stats()["max_width"] == N
 
 
+@pytest.mark.timeout(120)
+def test_dataflow_kernel_zero_pivot_is_reported_and_does_not_hang(ctor, monkeypatch):
+    """An exact zero as the very first pivot of a 193-order front in k_front_dag: the breakdown flag
+    comes back, every tile flag is still raised (the tasks behind it run on NaNs instead of waiting)."""
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    nv, ne, nc = 64, 96, 33
+    N, r, c, v = random_kkt(nv, ne, nc, 0.9, 293)
+    v = v.copy()
+    v[(r == 1) & (c == 1)] = 0.0
+    B = ctor(N, r, c, v, nvar=nv, nequ=ne, ncon=nc, ordering=1, refine_steps=0)
+    assert B.try_to_factorize(v, nv, ne, nc, EPS) is False
+    assert B.last_inertia[3] is True
+
+
 def test_empty_blocks_and_tiny_systems(ctor, oracle_cls):
     """ncon = 0 (unconstrained: no delta segment) and a 1 x 1 system."""
     N, r, c, v = random_kkt(12, 20, 0, 0.3, 34)
