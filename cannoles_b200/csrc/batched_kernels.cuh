@@ -52,6 +52,10 @@ constexpr int BF_STORE = 1, BF_SOLVE = 2, BF_NEGATE = 4, BF_LOAD = 8;
 #ifndef B2_BATCH_NT
 #define B2_BATCH_NT 256
 #endif
+#ifndef B2_BATCH_GRP
+#define B2_BATCH_GRP 4
+#endif
+constexpr int BATCH_GRP = B2_BATCH_GRP;  // 8-column steps per group of the dense panel factorization (see k_batched (b))
 constexpr int BATCH_NT = B2_BATCH_NT;   // threads per instance (one CTA per SM: shared memory holds one system)
 
 // C(t, j) -= sum_{q < K} A(t, q) B(j, q) for local columns j in [jbeg, jend) and local rows t in
@@ -247,12 +251,27 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
           panel_update<NW, false>(Pk, cbm, rowmap, abase, dd, Wd, c0, 0, w, m, nct, warp, lane);
         __syncthreads();
         B2_ACC(50, tq);
-        // (b) dense factorization of the panel, 8 columns at a time
+        // (b) dense factorization of the panel, 8 columns at a time, in groups of BATCH_GRP 8-column
+        // steps: inside a group a step is first brought up to date with the earlier steps of its
+        // group (left-looking, one tile column), the columns beyond the group get ONE rank-8 BATCH_GRP
+        // update per group -- a rank-8 update per step moved every entry of the trailing block
+        // through the packed storage (two index lookups per entry) for two DMMAs per tile
         for (int kb = 0; kb < w; kb += 8) {
           const int pw = min(8, w - kb);
+          const int gi = (kb >> 3) % BATCH_GRP, g0 = kb - 8 * gi;   // step inside its group, first column of the group
 #ifdef B2_TIMING
           tq = clock64();
 #endif
+          if (gi > 0) {
+            for (int q = tid; q < 8 * gi; q += NT) {
+              const int base = cbm[c0 + g0 + q];
+              abase[q] = base;
+              dd[q] = Pk[base + c0 + g0 + q];
+            }
+            __syncthreads();
+            panel_update<NW, false>(Pk, cbm, rowmap, abase, dd, Wd, c0, kb, kb + pw, m, 8 * gi, warp, lane);
+            __syncthreads();
+          }
           double g[8][8], rd[8], wv[8];
           B2_UNROLL
           for (int c = 0; c < 8; c++)
@@ -292,8 +311,16 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
 #ifdef B2_TIMING
           tq = clock64();
 #endif
-          if (kb + 8 < w)
-            panel_update<NW, true>(Pk, cbm, rowmap, abase, dd, Wd, c0, kb + 8, w, m, pw, warp, lane);
+          if (kb + 8 < w && (gi == BATCH_GRP - 1)) {   // end of a group: everything beyond it, rank-(8 BATCH_GRP)
+            const int K = kb + 8 - g0;
+            for (int q = tid; q < K; q += NT) {
+              const int base = cbm[c0 + g0 + q];
+              abase[q] = base;
+              dd[q] = Pk[base + c0 + g0 + q];
+            }
+            __syncthreads();
+            panel_update<NW, false>(Pk, cbm, rowmap, abase, dd, Wd, c0, kb + 8, w, m, K, warp, lane);
+          }
           __syncthreads();
           B2_ACC(53, tq);
         }
