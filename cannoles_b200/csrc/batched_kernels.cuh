@@ -59,11 +59,13 @@ constexpr int BATCH_GRP = B2_BATCH_GRP;  // 8-column steps per group of the dens
 constexpr int BATCH_NT = B2_BATCH_NT;   // threads per instance (one CTA per SM: shared memory holds one system)
 
 // C(t, j) -= sum_{q < K} A(t, q) B(j, q) for local columns j in [jbeg, jend) and local rows t in
-// [j, m) of one supernode panel, in 8 x 8 tiles; each warp takes strips of up to four row tiles.
+// [j, m) of one supernode panel, in 8 x 8 tiles; each warp takes strips of up to STRIP row tiles.
 //   A(t, q) = Pk[abase[q] + rowmap[t]]
 //   B(j, q) = FROM_W ? Wd[j * 8 + q] : Pk[abase[q] + c0 + j] * dd[q]
 //   C(t, j) = Pk[cbm[c0 + j] + rowmap[t]]
-template <int NW, bool FROM_W>
+// STRIP row tiles per task: 4 amortises the B fragment over more DMMA; 2 gives a one-tile-column
+// update (the in-group updates of the dense panel) enough tasks for all the warps.
+template <int NW, bool FROM_W, int STRIP = 4>
 __device__ __forceinline__ void panel_update(double* Pk, const int32_t* cbm, const int32_t* rowmap,
                                              const int32_t* abase, const double* dd, const double* Wd,
                                              int c0, int jbeg, int jend, int m, int K, int warp, int lane) {
@@ -71,35 +73,37 @@ __device__ __forceinline__ void panel_update(double* Pk, const int32_t* cbm, con
   const int ntj = (jend - jbeg + 7) >> 3, nti = (m - jbeg + 7) >> 3;
   int task = 0;
   for (int tj = 0; tj < ntj; tj++) {
-    for (int ti0 = tj; ti0 < nti; ti0 += 4, task++) {
+    for (int ti0 = tj; ti0 < nti; ti0 += STRIP, task++) {
       if (task % NW != warp) continue;
-      double acc[4][2];
+      double acc[STRIP][2];
       B2_UNROLL
-      for (int a = 0; a < 4; a++) { acc[a][0] = 0.0; acc[a][1] = 0.0; }
+      for (int a = 0; a < STRIP; a++) { acc[a][0] = 0.0; acc[a][1] = 0.0; }
       const int jb = jbeg + tj * 8 + g;                 // B-fragment column (local)
-      int ra[4];
+      int ra[STRIP];
       B2_UNROLL
-      for (int a = 0; a < 4; a++) {
+      for (int a = 0; a < STRIP; a++) {
         const int tr = jbeg + (ti0 + a) * 8 + g;        // A-fragment row (local)
         ra[a] = (ti0 + a < nti && tr < m) ? rowmap[tr] : -1;
       }
 #pragma unroll 2
       for (int q0 = 0; q0 < K; q0 += 4) {
         const int q = q0 + t4;
-        double bv = 0.0, av[4] = {0.0, 0.0, 0.0, 0.0};
+        double bv = 0.0, av[STRIP];
+        B2_UNROLL
+        for (int a = 0; a < STRIP; a++) av[a] = 0.0;
         if (q < K) {
           const int base = abase[q];
           if (jb < jend) bv = FROM_W ? Wd[jb * 8 + q] : Pk[base + c0 + jb] * dd[q];
           B2_UNROLL
-          for (int a = 0; a < 4; a++)
+          for (int a = 0; a < STRIP; a++)
             if (ra[a] >= 0) av[a] = Pk[base + ra[a]];
         }
         B2_UNROLL
-        for (int a = 0; a < 4; a++) dmma_8x8x4(acc[a][0], acc[a][1], av[a], bv);
+        for (int a = 0; a < STRIP; a++) dmma_8x8x4(acc[a][0], acc[a][1], av[a], bv);
       }
       const int cj = jbeg + tj * 8 + 2 * t4;            // C-fragment columns cj, cj + 1 (local)
       B2_UNROLL
-      for (int a = 0; a < 4; a++) {
+      for (int a = 0; a < STRIP; a++) {
         const int tr = jbeg + (ti0 + a) * 8 + g;
         if (ti0 + a >= nti || tr >= m) continue;
         const int gr = rowmap[tr];
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
               dd[q] = Pk[base + c0 + g0 + q];
             }
             __syncthreads();
-            panel_update<NW, false>(Pk, cbm, rowmap, abase, dd, Wd, c0, kb, kb + pw, m, 8 * gi, warp, lane);
+            panel_update<NW, false, 2>(Pk, cbm, rowmap, abase, dd, Wd, c0, kb, kb + pw, m, 8 * gi, warp, lane);
             __syncthreads();
           }
           double g[8][8], rd[8], wv[8];
