@@ -139,12 +139,25 @@ int BatchEngine::init(int dev, int64_t nbatch) {
       }
     }
   }
+  // per level: the supernodes the sequential loops of the kernel have work for
+  std::vector<int32_t> phw_ptr(1, 0), phw_sn, phb_ptr(1, 0), phb_sn;
+  for (int l = 0; l < S.nlevels; l++) {
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; q++) {
+      const int s = S.level_sn[q];
+      const int w = S.scol[s + 1] - S.scol[s];
+      if (!(w == 1 && ct_ptr[s + 1] == ct_ptr[s])) phw_sn.push_back(s);
+      if (w > 1) phb_sn.push_back(s);
+    }
+    phw_ptr.push_back((int32_t)phw_sn.size());
+    phb_ptr.push_back((int32_t)phb_sn.size());
+  }
   plan.N = N; plan.nnz = (int)S.nnz; plan.nsuper = S.nsuper; plan.nphase = S.nlevels;
   plan.npacked = (int)npacked; plan.nvar = (int)S.nvar; plan.nequ = (int)S.nequ; plan.ncon = (int)S.ncon;
   plan.nmulti = (int)multi_dst.size();
   if (up(S.perm, &plan.perm) || up(cbm, &plan.cbm) || up(S.scol, &plan.sc0) || up(rb_ptr, &plan.rb_ptr) ||
       up(rb_idx, &plan.rb_idx) || up(ct_ptr, &plan.ct_ptr) || up(ct_col, &plan.ct_col) ||
-      up(S.level_ptr, &plan.ph_ptr) || up(S.level_sn, &plan.ph_sn) || up(dst_single, &plan.dst_single) ||
+      up(S.level_ptr, &plan.ph_ptr) || up(S.level_sn, &plan.ph_sn) || up(phw_ptr, &plan.phw_ptr) ||
+      up(phw_sn, &plan.phw_sn) || up(phb_ptr, &plan.phb_ptr) || up(phb_sn, &plan.phb_sn) || up(dst_single, &plan.dst_single) ||
       up(multi_dst, &plan.multi_dst) || up(multi_ptr, &plan.multi_ptr) || up(multi_coo, &plan.multi_coo))
     return -1;
   if (alloc(&d_vals, (size_t)batch * S.nnz) || alloc(&d_rhs, (size_t)batch * N) ||

@@ -34,6 +34,12 @@ struct BatchPlanDev {
   const int32_t* ct_col;
   const int32_t* ph_ptr;     // nphase+1: supernodes grouped by tree level
   const int32_t* ph_sn;
+  // the same per level without the supernodes the sequential loops would only skip: 80 dependent
+  // plan reads per loop to skip the 79 leaves of config 5 cost 13 k cycles per loop (measured)
+  const int32_t* phw_ptr;    // nphase+1: supernodes that are not (width 1, no contributions): factorization, forward
+  const int32_t* phw_sn;
+  const int32_t* phb_ptr;    // nphase+1: supernodes of width > 1: backward
+  const int32_t* phb_sn;
   const int32_t* dst_single; // nnz: packed destination of a COO entry that is alone in its slot, else -1
   const int32_t* multi_dst;  // nmulti
   const int32_t* multi_ptr;  // nmulti+1 into multi_coo
@@ -230,11 +236,10 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
       __syncthreads();
       B2_TICK(32 + 2 * ph);
       // every other supernode of the level, one after the other, the whole CTA on each
-      for (int qs = q0; qs < q1; qs++) {
-        const int s = P.ph_sn[qs];
+      for (int qs = P.phw_ptr[ph]; qs < P.phw_ptr[ph + 1]; qs++) {
+        const int s = P.phw_sn[qs];
         const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
         const int nct = P.ct_ptr[s + 1] - P.ct_ptr[s];
-        if (w == 1 && nct == 0) continue;
         const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
         const int m = w + nrb;
         const int32_t* rb = P.rb_idx + P.rb_ptr[s];
@@ -364,11 +369,10 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   // forward: L y = b, level by level; a supernode first gathers the contributions of the
   // finished columns it depends on, then solves its own unit-lower pivot block
   for (int ph = 0; ph < P.nphase; ph++) {
-    for (int qs = P.ph_ptr[ph]; qs < P.ph_ptr[ph + 1]; qs++) {
-      const int s = P.ph_sn[qs];
+    for (int qs = P.phw_ptr[ph]; qs < P.phw_ptr[ph + 1]; qs++) {   // (a leaf has nothing to do going forward)
+      const int s = P.phw_sn[qs];
       const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
       const int nct = P.ct_ptr[s + 1] - P.ct_ptr[s];
-      if (w == 1 && nct == 0) continue;                  // a leaf: nothing to do going forward
       const int32_t* ct = P.ct_col + P.ct_ptr[s];
       for (int q = tid; q < nct; q += NT) {
         const int k = ct[q];
@@ -418,8 +422,10 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
       }
     }
   }
+  B2_TICK(43);
   for (int k = tid; k < N; k += NT) xs[k] /= Pk[cbm[k] + k];
   __syncthreads();
+  B2_TICK(44);
   // backward: L' x = z, levels in reverse; the rows below a supernode belong to higher levels
   // and are already final
   for (int ph = P.nphase - 1; ph >= 0; ph--) {
@@ -439,10 +445,10 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
       if (lane == 0) xs[c0] -= acc;
     }
     __syncthreads();
-    for (int qs = q0; qs < q1; qs++) {
-      const int s = P.ph_sn[qs];
+    B2_TICK(46 + (ph & 1));
+    for (int qs = P.phb_ptr[ph]; qs < P.phb_ptr[ph + 1]; qs++) {
+      const int s = P.phb_sn[qs];
       const int c0 = P.sc0[s], w = P.sc0[s + 1] - c0;
-      if (w == 1) continue;
       const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
       const int32_t* rb = P.rb_idx + P.rb_ptr[s];
       if (tid < w && nrb > 0) {                          // one thread per column over the rows below
@@ -485,6 +491,7 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
       }
     }
   }
+  B2_TICK(45);
   const double sign = (flags & BF_NEGATE) ? -1.0 : 1.0;
   double* dv = dout + (size_t)b * N;
   for (int k = tid; k < N; k += NT) dv[P.perm[k]] = sign * xs[k];
