@@ -33,7 +33,7 @@ class Stats(C.Structure):
 # every symbol include/cannoles_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
     "b2_last_error", "b2_version", "b2_device_count", "b2_analyze", "b2_factorize",
-    "b2_refactorize_shift", "b2_solve", "b2_factorize_dev", "b2_solve_dev", "b2_register_host",
+    "b2_refactorize_shift", "b2_factorize_retry", "b2_solve", "b2_factorize_dev", "b2_solve_dev", "b2_register_host",
     "b2_unregister_host", "b2_stats", "b2_last_timings", "b2_timer_start", "b2_timer_stop", "b2_last_sweeps", "b2_profile", "b2_front_sizes", "b2_get_perm", "b2_get_csc",
     "b2_get_nzval", "b2_get_d", "b2_set_option", "b2_free",
     "b2b_analyze", "b2b_factorize", "b2b_refactorize_shift", "b2b_solve", "b2b_factorize_dev",
@@ -55,6 +55,7 @@ def bind_library(path: str):
     lib.b2_factorize.argtypes = [vp, pd, C.c_double, p64, p64, p64, pi]
     lib.b2_factorize_dev.argtypes = [vp, vp, C.c_double, p64, p64, p64, pi]
     lib.b2_refactorize_shift.argtypes = [vp, C.c_double, C.c_double, C.c_double, p64, p64, p64, pi]
+    lib.b2_factorize_retry.argtypes = [vp, pd, C.c_double, C.c_double, p64, p64, p64, pi, pi]
     lib.b2_solve.argtypes = [vp, pd, pd, C.c_int, C.c_int, pd]
     lib.b2_solve_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, pd]
     lib.b2_register_host.argtypes = [vp, vp, C.c_size_t]

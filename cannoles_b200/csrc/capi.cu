@@ -59,7 +59,7 @@ int b2_analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* cols
   if (const char* e = getenv("B2_SOLVE_FORK")) h->eng.solve_fork = atoi(e);
   if (const char* e = getenv("B2_LOOKAHEAD")) h->eng.lookahead = atoi(e) != 0;
   if (const char* e = getenv("B2_DAG")) h->eng.use_dag = atoi(e) != 0;
-  if (const char* e = getenv("B2_DAG_MIN_NP")) h->eng.dag_min_np = atoi(e);
+  if (const char* e = getenv("B2_DAG_LEVEL_MAX")) h->eng.dag_level_max = atoi(e);
   if (const char* e = getenv("B2_DAG_EXCL_MAX")) h->eng.dag_excl_max = atoi(e);
   if (const char* e = getenv("B2_SOLVE_BIG_M")) h->eng.solve_big_m = atof(e);
   if (const char* e = getenv("B2_TINY_MAX_M")) h->eng.tiny_max_m = std::min(8, atoi(e));
@@ -89,6 +89,12 @@ int b2_refactorize_shift(b2_handle* h, double rho, double delta_or_nan, double e
                          int64_t* nzero, int64_t* nneg, int* breakdown) {
   if (!h) return fail("b2_refactorize_shift: NULL handle");
   return h->eng.refactorize_shift(rho, delta_or_nan, eig_tol, npos, nzero, nneg, breakdown);
+}
+
+int b2_factorize_retry(b2_handle* h, const double* vals, double rho, double eig_tol, int64_t* npos,
+                       int64_t* nzero, int64_t* nneg, int* breakdown, int* speculation_held) {
+  if (!h || !vals) return fail("b2_factorize_retry: NULL argument");
+  return h->eng.factorize_retry(vals, rho, eig_tol, npos, nzero, nneg, breakdown, speculation_held);
 }
 
 int b2_solve(b2_handle* h, const double* rhs, double* d_out, int negate, int refine_steps, double* relres) {

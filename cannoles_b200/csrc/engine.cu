@@ -55,24 +55,49 @@ int Engine::build_plan() {
   nsflag = 0;
   fact_launches.clear(); fwd_launches.clear(); bwd_launches.clear();
   n_small = n_large = 0;
-  int dag_tasks = 0;
   std::vector<char> front_dag(S.nsuper, 0);
   auto front_m = [&](int s) { return (int)(S.rptr[s + 1] - S.rptr[s]); };
   auto front_w = [&](int s) { return (int)(S.scol[s + 1] - S.scol[s]); };
+  // Cross-level dataflow: the top of the assembly tree -- the highest run of levels with at most
+  // dag_level_max fronts each, if it holds a front of the tiled path at all -- is ONE k_front_dag
+  // launch: every front of those levels is cut into NB x NB tile tasks, the extend-add is a task
+  // kind, and a parent waits for ITS children only (counters), not for a level.
+  dag_from_level = S.nlevels;
+  if (use_dag) {
+    int l = S.nlevels;
+    while (l > 0 && S.level_ptr[l] - S.level_ptr[l - 1] <= dag_level_max) l--;
+    bool any_large = false;
+    for (int q = S.level_ptr[l]; q < S.level_ptr[S.nlevels] && !any_large; q++)
+      any_large = front_m(S.level_sn[q]) > (int)small_max_m;
+    if (any_large) dag_from_level = l;
+  }
+  struct DagFront { int s, m, w, np, nrb; int32_t fb, df, tbase, abase; };
+  struct TlEnt { int64_t gid; int32_t ce, ia, iz, ja, jz; };
+  std::vector<TlEnt> tl_tmp;                        // (tile, child) pairs in front / child order
+  std::vector<int32_t> tl_cnt, ta_ptr;
+  std::vector<DagFront> dagf;                       // fronts of the dataflow launch, in level order
+  std::vector<int32_t> dag_of(S.nsuper, -1);        // front -> its record
+  std::vector<int32_t> items_dag;                   // task records (8 ints each), level by level
+  std::vector<int32_t> dfr;
+  Launch G; G.kind = LK_DAG;
   std::vector<size_t> fstart, sstart, bstart;   // first launch of every level in the three lists
   for (int l = 0; l < S.nlevels; l++) {
     fstart.push_back(fact_launches.size()); sstart.push_back(fwd_launches.size()); bstart.push_back(bwd_launches.size());
     std::vector<int32_t> small[4], large, sol[4], big, tiny[2], tsol[2];
     int small_mmax[4] = {0, 0, 0, 0}, sol_mmax[4] = {0, 0, 0, 0};
+    const bool dagl = l >= dag_from_level;          // a level of the dataflow launch: no other factorization launch
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; q++) {
       int s = S.level_sn[q];
       int m = front_m(s);
       if (m <= tiny_max_m && m <= (int)small_max_m) {   // one thread per front, factorization and solves
         tiny[m <= 4 ? 0 : 1].push_back(s);
-        n_small++;
+        if (dagl) { large.push_back(s); n_large++; } else n_small++;
         continue;
       }
-      if (m <= (int)small_max_m) {
+      if (dagl) {
+        large.push_back(s);
+        n_large++;
+      } else if (m <= (int)small_max_m) {
         int c = small_class(m);
         small[c].push_back(s);
         small_mmax[c] = std::max(small_mmax[c], m);
@@ -95,7 +120,7 @@ int Engine::build_plan() {
       if (tiny[c].empty()) continue;
       Launch L; L.kind = LK_FRONT_TINY; L.cls = c; L.off = (int64_t)items.size(); L.count = (int)tiny[c].size();
       items.insert(items.end(), tiny[c].begin(), tiny[c].end());
-      fact_launches.push_back(L);
+      if (!dagl) fact_launches.push_back(L);
       L.kind = LK_FWD_TINY; fwd_launches.push_back(L);
       L.kind = LK_BWD_TINY; bwd_launches.push_back(L);
     }
@@ -170,103 +195,148 @@ int Engine::build_plan() {
       bwd_launches.push_back(Bk);
     }
     if (large.empty()) continue;
-    {
-      Launch L; L.kind = LK_ASSEMBLE_LARGE; L.off = (int64_t)items.size();
-      for (int s : large) {
-        int m = front_m(s);
-        const int acols = m <= 128 ? 16 : 8, arows = ASM_TILE / acols;   // tile shape of this front
-        int ncb = (m + acols - 1) / acols, nrb = (m + arows - 1) / arows;
-        // per destination column: the (child descriptor, child column) pairs that land on it, children
-        // ascending (the extend-add order)
-        const int64_t gbase = (int64_t)asm_cptr.size() - 1;   // global id of this front's column 0
-        std::vector<std::vector<int32_t>> percol(m);
-        for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
-          int c = S.child_idx[q];
-          int wc = front_w(c);
-          const int32_t* relc = &S.rel[S.rptr[c] + wc];
-          int rc = front_m(c) - wc;
-          if (rc == 0) continue;
-          const int32_t ce = (int32_t)asm_rc.size();
-          asm_rc.push_back(rc);
-          asm_off.push_back(S.rptr[c] + wc); asm_off.push_back(S.cbptr[c]);
-          for (int j = 0; j < rc; j++) { percol[relc[j]].push_back(ce); percol[relc[j]].push_back(j); }
+    // extend-add items of one tiled front (8 ints each, see assemble_tile_body); for a front of the
+    // dataflow launch also the expected number of items per 64-column group of the front
+    auto asm_items = [&](int s, std::vector<int32_t>& out, int df, int32_t* expect) -> int {
+      int cnt = 0;
+      int m = front_m(s);
+      const int acols = m <= 128 ? 16 : 8, arows = ASM_TILE / acols;   // tile shape of this front
+      int ncb = (m + acols - 1) / acols, nrb = (m + arows - 1) / arows;
+      // per destination column: the (child descriptor, child column) pairs that land on it, children
+      // ascending (the extend-add order)
+      const int64_t gbase = (int64_t)asm_cptr.size() - 1;   // global id of this front's column 0
+      std::vector<std::vector<int32_t>> percol(m);
+      for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
+        int c = S.child_idx[q];
+        int wc = front_w(c);
+        const int32_t* relc = &S.rel[S.rptr[c] + wc];
+        int rc = front_m(c) - wc;
+        if (rc == 0) continue;
+        const int32_t ce = (int32_t)asm_rc.size();
+        asm_rc.push_back(rc);
+        asm_off.push_back(S.rptr[c] + wc); asm_off.push_back(S.cbptr[c]);
+        for (int j = 0; j < rc; j++) { percol[relc[j]].push_back(ce); percol[relc[j]].push_back(j); }
+      }
+      for (int J = 0; J < m; J++) {
+        asm_ent.insert(asm_ent.end(), percol[J].begin(), percol[J].end());
+        asm_cptr.push_back((int64_t)asm_ent.size() / 2);
+      }
+      const int32_t* apos = S.amap_pos.data() + S.amap_ptr[s];
+      const int64_t na = S.amap_ptr[s + 1] - S.amap_ptr[s];
+      const int w = front_w(s);
+      for (int cb = 0; cb < ncb; cb++) {
+        // A entries of pivot columns [j0, min(je, w)): positions row + col * m, sorted
+        int j0 = cb * acols, je = std::min(j0 + acols, m);
+        int qa = 0, qb = 0;
+        if (j0 < w) {
+          qa = (int)(std::lower_bound(apos, apos + na, j0 * m) - apos);
+          qb = (int)(std::lower_bound(apos, apos + na, std::min(je, w) * m) - apos);
         }
-        for (int J = 0; J < m; J++) {
-          asm_ent.insert(asm_ent.end(), percol[J].begin(), percol[J].end());
-          asm_cptr.push_back((int64_t)asm_ent.size() / 2);
-        }
-        const int32_t* apos = S.amap_pos.data() + S.amap_ptr[s];
-        const int64_t na = S.amap_ptr[s + 1] - S.amap_ptr[s];
-        const int w = front_w(s);
-        for (int cb = 0; cb < ncb; cb++) {
-          // A entries of pivot columns [j0, min(je, w)): positions row + col * m, sorted
-          int j0 = cb * acols, je = std::min(j0 + acols, m);
-          int qa = 0, qb = 0;
-          if (j0 < w) {
-            qa = (int)(std::lower_bound(apos, apos + na, j0 * m) - apos);
-            qb = (int)(std::lower_bound(apos, apos + na, std::min(je, w) * m) - apos);
-          }
-          for (int rb = 0; rb < nrb; rb++) {
-            if ((rb + 1) * arows <= cb * acols) continue;   // tile entirely above the diagonal
-            items.push_back(s); items.push_back(j0); items.push_back(rb * arows); items.push_back((int32_t)(gbase + j0));
-            items.push_back(qa); items.push_back(qb); items.push_back(acols); items.push_back(arows);
-            L.count++;
-          }
+        for (int rb = 0; rb < nrb; rb++) {
+          if ((rb + 1) * arows <= cb * acols) continue;   // tile entirely above the diagonal
+          out.push_back(s); out.push_back(j0); out.push_back((rb * arows) | (3 << 16)); out.push_back((int32_t)(gbase + j0));
+          out.push_back(qa); out.push_back(qb); out.push_back(acols | (arows << 16)); out.push_back(df);
+          if (expect) expect[j0 / 64]++;
+          cnt++;
         }
       }
-      fact_launches.push_back(L);
-    }
-    int level_np = 0;
-    for (int s : large) level_np = std::max(level_np, (front_w(s) + NB - 1) / NB);
-    // measured on C4: the dataflow launch wins where fronts have several pivot blocks (a chain of
-    // launches otherwise); levels made of thousands of one-block fronts are faster on the chain
-    if (use_dag && level_np >= dag_min_np) {
-      for (int s : large) front_dag[s] = 1;
-      // tasks over the NB x NB tiles (I, J), I >= J, of every tiled front of the level (see k_front_dag)
-      Launch G; G.kind = LK_DAG; G.off = (int64_t)items.size(); G.jb = ndag++;
-      struct FG { int s, nrb; int32_t fb; int m; };
-      std::vector<FG> fg;
+      return cnt;
+    };
+    if (dagl) {
+      // tasks over the NB x NB tiles (I, J), I >= J, of every front of the level (see k_front_dag)
+      std::vector<DagFront> fg;
       for (int s : large) {
         int w = front_w(s), m = front_m(s);
         int np = (w + NB - 1) / NB, nrb = np + (m - w + NB - 1) / NB;
-        if (ntflag + (int64_t)np * (nrb + 1) >= (int64_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "too many tiles"); return -1; }
-        fg.push_back({s, nrb, (int32_t)ntflag, m});
+        if (m >= 65536 || ntflag + (int64_t)np * (nrb + 1) >= (int64_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "too many tiles"); return -1; }
+        fg.push_back({s, m, w, np, nrb, (int32_t)ntflag, 0, 0, 0});
         ntflag += (int64_t)np * (nrb + 1);   // one flag per tile of the pivot columns + one per ypre task
       }
-      std::stable_sort(fg.begin(), fg.end(), [](const FG& a, const FG& b) { return a.m > b.m; });
-      // ticket order = waves of the tile DAG over all fronts of the level (a topological order):
-      // wave 2d holds what can start once pivot block d-1 is factored -- the chain task of block d
-      // (first: it is the critical path) and the tiles of column d-1; 2d+1 the ypre task of block
-      // d+1; the tiles of the contribution block follow the last column (wave 2 np + 1)
-      struct TK { int key, pri; int32_t s, I, code, fb; };
+      std::stable_sort(fg.begin(), fg.end(), [](const DagFront& a, const DagFront& b) { return a.m > b.m; });
+      for (DagFront& f : fg) {
+        f.df = (int32_t)dagf.size();
+        dag_of[f.s] = f.df;
+        front_dag[f.s] = 1;
+        int nch = 0;
+        for (int q = S.child_ptr[f.s]; q < S.child_ptr[f.s + 1]; q++) nch += dag_of[S.child_idx[q]] >= 0;
+        const int nq = f.nrb - f.np;
+        dfr.push_back(0); dfr.push_back(nq * (nq + 1) / 2); dfr.push_back(-1); dfr.push_back(nch);
+        // extend-add lists: per tile (I, J) of the front the children that land on it, with the child
+        // rows / columns that fall into row block I / column block J (rel[] is ascending: ranges)
+        f.tbase = (int32_t)tl_cnt.size();
+        tl_cnt.resize(tl_cnt.size() + (size_t)f.nrb * f.nrb, 0);
+        auto blk_lo = [&](int b) { return b < f.np ? b * NB : f.w + (b - f.np) * NB; };
+        std::vector<int> ca(f.nrb + 1);
+        for (int q = S.child_ptr[f.s]; q < S.child_ptr[f.s + 1]; q++) {
+          const int c = S.child_idx[q];
+          const int wc = front_w(c), rc = front_m(c) - wc;
+          if (rc == 0) continue;
+          const int32_t* relc = &S.rel[S.rptr[c] + wc];
+          const int32_t ce = (int32_t)asm_rc.size();
+          asm_rc.push_back(rc);
+          asm_off.push_back(S.rptr[c] + wc); asm_off.push_back(S.cbptr[c]);
+          for (int b = 0, k = 0; b <= f.nrb; b++) {       // ca[b] = first child row in block >= b
+            const int lo = b < f.nrb ? blk_lo(b) : f.m;
+            while (k < rc && relc[k] < lo) k++;
+            ca[b] = k;
+          }
+          for (int bj = 0; bj < f.nrb; bj++) {
+            if (ca[bj] == ca[bj + 1]) continue;
+            for (int bi = bj; bi < f.nrb; bi++) {
+              if (ca[bi] == ca[bi + 1]) continue;
+              tl_tmp.push_back({(int64_t)f.tbase + (int64_t)bj * f.nrb + bi, ce, ca[bi], ca[bi + 1], ca[bj], ca[bj + 1]});
+              tl_cnt[(size_t)f.tbase + (size_t)bj * f.nrb + bi]++;
+            }
+          }
+        }
+        // A entries per 64-column block (amap is sorted by position = row + col * m)
+        f.abase = (int32_t)ta_ptr.size();
+        {
+          const int32_t* apos = S.amap_pos.data() + S.amap_ptr[f.s];
+          const int64_t na = S.amap_ptr[f.s + 1] - S.amap_ptr[f.s];
+          for (int b = 0; b <= f.nrb; b++) {
+            const int col = b < f.np ? b * NB : f.w;      // blocks of the contribution block hold no A entry
+            ta_ptr.push_back((int32_t)(std::lower_bound(apos, apos + na, (int64_t)col * f.m > INT32_MAX ? INT32_MAX : col * f.m) - apos));
+          }
+        }
+        dagf.push_back(f);
+      }
+      // ticket order inside a level = waves of the tile DAG over all its fronts (a topological
+      // order): wave 2d holds what can start once pivot block d-1 is factored -- the chain task of
+      // block d (first: it is the critical path) and the tiles of column d-1; 2d+1 the ypre task of
+      // block d+1; the tiles of the contribution block follow the last column (wave 2 np + 1)
+      struct TK { int key, pri; int32_t s, I, code, fb, df, tbase, abase; };
       std::vector<TK> tks;
-      for (const FG& f : fg) {
-        const int np = (front_w(f.s) + NB - 1) / NB;
+      for (const DagFront& f : fg) {
+        const int np = f.np;
         for (int J = 0; J < f.nrb; J++)
           for (int I = J; I < f.nrb; I++) {
-            if (J >= np) { tks.push_back({2 * np + 1, 1, f.s, I, J, f.fb}); continue; }
+            if (J >= np) { tks.push_back({2 * np + 1, 1, f.s, I, J, f.fb, f.df, f.tbase, f.abase}); continue; }
             if (I == J) {
-              if (J == 0) tks.push_back({0, 0, f.s, 0, 0, f.fb});
+              if (J == 0) tks.push_back({0, 0, f.s, 0, 0, f.fb, f.df, f.tbase, f.abase});
               continue;                                      // J > 0: part of the chain task of block J
             }
             if (I == J + 1 && I < np) {                      // chain task: tiles (I, I-1) and (I, I) ...
-              tks.push_back({2 * I, 0, f.s, I, I | (1 << 16), f.fb});
+              tks.push_back({2 * I, 0, f.s, I, I | (1 << 16), f.fb, f.df, f.tbase, f.abase});
               // ... after the task that applies the pivot blocks p < I-1 to (I, I)
-              if (I >= 2) tks.push_back({2 * (I - 1) + 1, 1, f.s, I, I | (2 << 16), f.fb});
+              if (I >= 2) tks.push_back({2 * (I - 1) + 1, 1, f.s, I, I | (2 << 16), f.fb, f.df, f.tbase, f.abase});
               continue;
             }
-            tks.push_back({2 * (J + 1), 1, f.s, I, J, f.fb});
+            tks.push_back({2 * (J + 1), 1, f.s, I, J, f.fb, f.df, f.tbase, f.abase});
           }
       }
       std::stable_sort(tks.begin(), tks.end(), [](const TK& a, const TK& b) { return a.key != b.key ? a.key < b.key : a.pri < b.pri; });
       for (const TK& t : tks) {
-        items.push_back(t.s); items.push_back(t.I); items.push_back(t.code); items.push_back(t.fb);
+        const int32_t rec[8] = {t.s, t.I, t.code, t.fb, t.tbase, t.abase, 0, t.df};
+        items_dag.insert(items_dag.end(), rec, rec + 8);
         G.count++;
       }
-      G.mode = dag_tasks;   // index of its first task among all dataflow tasks (trace slots)
-      dag_tasks += G.count;
-      if (G.count) fact_launches.push_back(G);
       continue;
+    }
+    {
+      Launch L; L.kind = LK_ASSEMBLE_LARGE; L.off = (int64_t)items.size();
+      for (int s : large) L.count += asm_items(s, items, 0, nullptr);
+      fact_launches.push_back(L);
     }
     int wmax = 0;
     for (int s : large) wmax = std::max(wmax, front_w(s));
@@ -346,6 +416,39 @@ int Engine::build_plan() {
     for (size_t i = sstart[l]; i < sstart[l + 1]; i++) { fwd_launches[i].level = l; fwd_launches[i].branch = branch_of(fwd_launches[i]); }
     for (size_t i = bstart[l]; i < bstart[l + 1]; i++) { bwd_launches[i].level = l; bwd_launches[i].branch = branch_of(bwd_launches[i]); }
   }
+  // the dataflow launch of the top of the tree: parents' records, absolute counter offsets
+  ndag = 0; ndcnt = 0;
+  if (G.count > 0) {
+    const int ndf = (int)dagf.size();
+    for (const DagFront& f : dagf) {
+      const int p = S.sparent[f.s];
+      if (p >= 0) dfr[4 * (size_t)f.df + 2] = dag_of[p];
+    }
+    plan.dcnt_cb = 0; plan.dcnt_ch = ndf;
+    ndcnt = 2 * (int64_t)ndf;
+    if ((int64_t)items.size() + (int64_t)items_dag.size() >= (int64_t)INT32_MAX * 4) { snprintf(g_last_error, sizeof(g_last_error), "too many dataflow tasks"); return -1; }
+    G.off = (int64_t)items.size();
+    items.insert(items.end(), items_dag.begin(), items_dag.end());
+    G.level = dag_from_level; G.branch = 9; G.jb = 0; G.mode = 0;
+    fact_launches.push_back(G);
+    ndag = 1;
+  }
+  if (upload(&d_dfr, dfr, bytes_device)) return -1;
+  {
+    // per-tile child lists: counting sort of the (tile, child) pairs by tile (children stay ascending)
+    if (tl_tmp.size() >= (size_t)INT32_MAX / 8) { snprintf(g_last_error, sizeof(g_last_error), "too many extend-add pairs"); return -1; }
+    std::vector<int32_t> tl_ptr(tl_cnt.size() + 1, 0);
+    for (size_t i = 0; i < tl_cnt.size(); i++) tl_ptr[i + 1] = tl_ptr[i] + tl_cnt[i];
+    std::vector<int32_t> fill(tl_ptr.begin(), tl_ptr.end() - 1), tl_ent(6 * tl_tmp.size(), 0);
+    for (const TlEnt& e : tl_tmp) {
+      int32_t* d = &tl_ent[6 * (size_t)fill[e.gid]++];
+      d[0] = e.ce; d[1] = e.ia; d[2] = e.iz; d[3] = e.ja; d[4] = e.jz;
+    }
+    if (upload(&d_tl_ptr, tl_ptr, bytes_device)) return -1;
+    if (upload(&d_tl_ent, tl_ent, bytes_device)) return -1;
+    if (upload(&d_ta_ptr, ta_ptr, bytes_device)) return -1;
+    plan.dfr = d_dfr; plan.tl_ptr = d_tl_ptr; plan.tl_ent = d_tl_ent; plan.ta_ptr = d_ta_ptr;
+  }
   // staging area of the factored diagonal blocks + the write-back launch that ends a factorization
   {
     std::vector<int64_t> dsptr(S.nsuper + 1, 0);
@@ -353,7 +456,7 @@ int Engine::build_plan() {
     int64_t off = 0;
     for (int s = 0; s < S.nsuper; s++) {
       dsptr[s] = off;
-      if (front_m(s) <= (int)small_max_m) continue;
+      if (front_m(s) <= (int)small_max_m && !front_dag[s]) continue;
       int nblk = (front_w(s) + NB - 1) / NB;
       if (!front_dag[s])   // k_front_dag writes the diagonal blocks in place
         for (int bi = 0; bi < nblk; bi++) { items.push_back(s); items.push_back(bi); W.count++; }
@@ -422,7 +525,8 @@ int Engine::build_plan() {
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
   if (dalloc(&d_ypub, (size_t)(2 * S.N), bytes_device)) return -1;   // forward | backward publication slots
   plan.sb_ptr = d_sb_ptr; plan.sb_src = d_sb_src; plan.sb_flag = d_sb_flag;
-  if (dalloc(&d_tflag, (size_t)(ntflag + ndag + 1), bytes_device)) return -1;   // tile flags | ticket counters
+  if (dalloc(&d_tflag, (size_t)(ntflag + 1 + ndcnt), bytes_device)) return -1;   // tile flags | ticket counter | counters
+  plan.dcnt = d_tflag + ntflag + 1;
   std::reverse(bwd_launches.begin(), bwd_launches.end());
   if (upload(&d_items, items, bytes_device)) return -1;
   return 0;
@@ -518,8 +622,12 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_ta_ptr, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (h_mismatch) cudaFreeHost(h_mismatch);
+  if (cstream) cudaStreamDestroy(cstream);
+  if (ev_cmp) cudaEventDestroy(ev_cmp);
+  if (ev_cfork) cudaEventDestroy(ev_cfork);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_scalars) cudaFreeHost(h_scalars);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -563,10 +671,10 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       // FP64 pipe with a neighbour's update (measured: LDL^T of a 64 x 64 tile 16 -> 11.5 us)
       if (L.count <= dag_excl_max)
         B2_LAUNCH(k_front_dag, std::min(L.count, dag_ctas / 2), 256, DAG_SMEM_EXCL, st, plan, it, L.count, d_tflag,
-                  d_tflag + ntflag + L.jb, L.mode);
+                  d_tflag + ntflag, L.mode);
       else
         B2_LAUNCH(k_front_dag, std::min(L.count, dag_ctas), 256, DAG_SMEM, st, plan, it, L.count, d_tflag,
-                  d_tflag + ntflag + L.jb, L.mode);
+                  d_tflag + ntflag, L.mode);
       break;
     case LK_FWD:
       if (L.cls == 0) { auto kfn = k_fwd<32, FPB32>; B2_LAUNCH(kfn, (L.count + FPB32 - 1) / FPB32, 32 * FPB32, L.smem * FPB32, st, plan, it, L.count, d_x, d_upd, L.smem); }
@@ -669,7 +777,7 @@ int Engine::run_list(const std::vector<Launch>& LL, bool allow_fork) {
 
 int Engine::run_factor_launches() {
   // tile flags and ticket counters of the dataflow launches
-  if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + ndag) * sizeof(int), stream));
+  if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + 1 + ndcnt) * sizeof(int), stream));
   return run_list(fact_launches, true);
 }
 
@@ -706,7 +814,7 @@ int Engine::profile(int which, int max, int* kinds, int* cls, int* counts, doubl
   for (int rep = 0; rep < 2; rep++) {   // second pass is the warm one
     if (which == 0) {
       B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
-      if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + ndag) * sizeof(int), stream));
+      if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + 1 + ndcnt) * sizeof(int), stream));
     } else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
     B2_CUDA_OK(cudaEventRecord(evs[0], stream));
     for (size_t i = 0; i < LL.size(); i++) {
@@ -824,6 +932,49 @@ int Engine::refactorize_shift(double rho, double delta, double eig_tol, int64_t*
   if (S.ncon > 0 && delta == delta)
     B2_LAUNCH(k_diag_shift, (int)((S.ncon + 255) / 256), 256, 0, stream, (int)S.ncon, d_delta_slot, d_delta_base, -delta, d_nzval);
   return assemble_and_factor(eig_tol, npos, nzero, nneg, breakdown, false);
+}
+
+// A rho retry that cannot go wrong: same result as factorize_host(vals), bit for bit, whatever the
+// caller did to vals.  The caller believes that only the trailing rho segment changed since the last
+// upload and now holds the constant `rho` (the protocol of newton_system!, src/CaNNOLeS.jl:1029-1043):
+// the shifted matrix is factorized right away while, on a copy stream, vals is uploaded into the
+// second buffer and compared on the device with the previous upload.  If the belief was wrong the
+// factorization is redone from the fresh upload (assembly included).
+int Engine::factorize_retry(const double* vals, double rho, double eig_tol, int64_t* npos, int64_t* nzero,
+                            int64_t* nneg, int* breakdown, int* speculation_held) {
+  const Symbolic& S = sym;
+  if (speculation_held) *speculation_held = 0;
+  if (!S.shift_ok || !have_vals || S.nvar == 0) return factorize_host(vals, eig_tol, npos, nzero, nneg, breakdown);
+  B2_CUDA_OK(cudaSetDevice(device));
+  if (!d_vals2) {
+    B2_CUDA_OK(cudaMalloc((void**)&d_vals2, (size_t)S.nnz * sizeof(double)));
+    B2_CUDA_OK(cudaMalloc((void**)&d_mismatch, sizeof(int)));
+    B2_CUDA_OK(cudaMallocHost((void**)&h_mismatch, sizeof(int)));
+    B2_CUDA_OK(cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
+    B2_CUDA_OK(cudaEventCreateWithFlags(&ev_cmp, cudaEventDisableTiming));
+    B2_CUDA_OK(cudaEventCreateWithFlags(&ev_cfork, cudaEventDisableTiming));
+    bytes_device += (double)S.nnz * sizeof(double);
+  }
+  // the copy stream starts after whatever the main stream still does with d_vals (nothing reads d_vals2)
+  B2_CUDA_OK(cudaEventRecord(ev_cfork, stream));
+  B2_CUDA_OK(cudaStreamWaitEvent(cstream, ev_cfork, 0));
+  B2_CUDA_OK(cudaMemsetAsync(d_mismatch, 0, sizeof(int), cstream));
+  B2_CUDA_OK(cudaMemcpyAsync(d_vals2, vals, (size_t)S.nnz * sizeof(double), cudaMemcpyHostToDevice, cstream));
+  {
+    const int nb = (int)std::min<int64_t>((S.nnz + 255) / 256, 2368);
+    B2_LAUNCH(k_vals_compare, nb, 256, 0, cstream, S.nnz, S.nnz - S.nvar, d_vals, d_vals2, rho, d_mismatch);
+  }
+  B2_CUDA_OK(cudaMemcpyAsync(h_mismatch, d_mismatch, sizeof(int), cudaMemcpyDeviceToHost, cstream));
+  B2_CUDA_OK(cudaEventRecord(ev_cmp, cstream));
+  if (refactorize_shift(rho, std::nan(""), eig_tol, npos, nzero, nneg, breakdown)) return -1;
+  B2_CUDA_OK(cudaEventSynchronize(ev_cmp));
+  std::swap(d_vals, d_vals2);          // d_vals = what the caller holds now, in both cases
+  if (*h_mismatch == 0) {
+    if (speculation_held) *speculation_held = 1;
+    return 0;
+  }
+  B2_CUDA_OK(cudaEventRecord(ev[0], stream));
+  return assemble_and_factor(eig_tol, npos, nzero, nneg, breakdown, true);
 }
 
 int Engine::solve_core(const double* d_b, double* d_o, int negate, int refine_steps, double* relres) {

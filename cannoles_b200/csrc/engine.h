@@ -58,7 +58,10 @@ struct Engine {
   // dataflow factorization of the tiled fronts (k_front_dag: one launch per tree level instead of a
   // k_trsm / k_update launch pair per 64-column pivot block); B2_DAG=0 selects the launch chain
   bool use_dag = true;
-  int dag_min_np = 4;          // ... on the tree levels whose widest front has at least this many pivot blocks (B2_DAG_MIN_NP)
+  int dag_level_max = 600;     // ... covering the highest run of tree levels with at most this many fronts each (B2_DAG_LEVEL_MAX)
+  int dag_from_level = 0;      // first level of the dataflow launch (== nlevels: none)
+  int64_t ndcnt = 0;           // counters of the dataflow launch (after the tile flags and the ticket)
+  int32_t *d_dfr = nullptr, *d_tl_ptr = nullptr, *d_tl_ent = nullptr, *d_ta_ptr = nullptr;
   int dag_excl_max = 0;        // k_front_dag launches with at most this many tasks run one CTA per SM (B2_DAG_EXCL_MAX)
   int dag_ctas = 0;            // CTAs of a k_front_dag launch (resident CTAs of the device)
   int64_t ntflag = 0;          // tile flags of all tiled fronts; the ticket counters of the launches follow them
@@ -73,6 +76,13 @@ struct Engine {
   // device buffers
   int32_t *d_slot_ptr = nullptr, *d_coo_sorted = nullptr;
   double *d_vals = nullptr, *d_nzval = nullptr;
+  // speculative rho retry: the caller's values are uploaded to a second buffer on a copy stream and
+  // compared with the previous upload while the shifted matrix is already being factorized
+  double* d_vals2 = nullptr;
+  int* d_mismatch = nullptr;
+  int* h_mismatch = nullptr;
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_cmp = nullptr, ev_cfork = nullptr;
   int32_t *d_rho_slot = nullptr, *d_delta_slot = nullptr;
   double *d_rho_base = nullptr, *d_delta_base = nullptr;
   int32_t *d_scol = nullptr, *d_rowidx = nullptr, *d_rel = nullptr, *d_child_ptr = nullptr,
@@ -130,6 +140,8 @@ struct Engine {
                     int64_t* nneg, int* breakdown);
   int refactorize_shift(double rho, double delta, double eig_tol, int64_t* npos, int64_t* nzero,
                         int64_t* nneg, int* breakdown);
+  int factorize_retry(const double* vals, double rho, double eig_tol, int64_t* npos, int64_t* nzero,
+                      int64_t* nneg, int* breakdown, int* speculation_held);
   int solve_core(const double* d_b, double* d_o, int negate, int refine_steps, double* relres);
   int solve_host(const double* rhs, double* out, int negate, int refine_steps, double* relres);
 };

@@ -65,6 +65,21 @@ __global__ void __launch_bounds__(256) k_diag_shift(int n, const int32_t* __rest
   nzval[slots[i]] = base[i] + shift;
 }
 
+// Validation of a speculative rho retry (Engine::factorize_retry): flag[0] = 1 unless `fresh` (the
+// caller's values, just uploaded) equals `prev` (the values of the last upload) bit for bit outside
+// the trailing rho segment and holds exactly `rho` inside it.
+__global__ void __launch_bounds__(256) k_vals_compare(int64_t n, int64_t nhead, const double* __restrict__ prev,
+                                                      const double* __restrict__ fresh, double rho,
+                                                      int* __restrict__ flag) {
+  const long long rbits = __double_as_longlong(rho);
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const long long f = __double_as_longlong(fresh[i]);
+    bad = bad || (i < nhead ? f != __double_as_longlong(prev[i]) : f != rbits);
+  }
+  if (bad) flag[0] = 1;
+}
+
 // ------------------------------------------------------------------------------------------
 // (2a) small fronts: the whole m x m front lives in shared memory.
 // zero -> scatter A -> extend-add children (fixed order, deterministic) -> eliminate w pivots
@@ -233,24 +248,24 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_front_tiny(PlanDev P, const int
 // pairs land on a destination column and where their data lives is precomputed on the host
 // (asm_cptr / asm_ent / asm_rc / asm_off): a front at the top of the tree has hundreds of small
 // children and scanning them all per tile was the whole cost of the first version of this kernel.
-__global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t* __restrict__ items, int nitems) {
-  const int b = blockIdx.x;
-  if (b >= nitems) return;
-  const int s = items[8 * b], j0 = items[8 * b + 1], i0 = items[8 * b + 2];
-  const int gcb = items[8 * b + 3];
-  const int ncols = items[8 * b + 6], nrows = items[8 * b + 7];   // tile shape: ncols * nrows <= ASM_TILE
+// (the body is shared with the extend-add tasks of k_front_dag; `it` = the 8 ints of the item, the
+// row origin in the low 16 bits of it[2], the tile shape packed in it[6] = ncols | nrows << 16)
+__device__ __forceinline__ void assemble_tile_body(const PlanDev& P, const int32_t* __restrict__ it, double* T) {
+  const int s = it[0], j0 = it[1], i0 = it[2] & 0xffff;
+  const int gcb = it[3];
+  const int ncols = it[6] & 0xffff, nrows = it[6] >> 16;   // tile shape: ncols * nrows <= ASM_TILE
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
   const int64_t r0 = P.rptr[s];
   const int m = (int)(P.rptr[s + 1] - r0);
   const int r = m - w;
   const int je = min(j0 + ncols, m), ie = min(i0 + nrows, m);
-  __shared__ double T[ASM_TILE];   // T[(j - j0) * nrows + (i - i0)]
+  // T[(j - j0) * nrows + (i - i0)]: ASM_TILE doubles of shared memory
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < ncols * nrows; idx += 256) T[idx] = 0.0;
   __syncthreads();
   {  // A entries of the tile's pivot columns: range precomputed on the host (amap is sorted by position)
     const int64_t a0 = P.amap_ptr[s];
-    const int64_t qa = a0 + items[8 * b + 4], qb = a0 + items[8 * b + 5];
+    const int64_t qa = a0 + it[4], qb = a0 + it[5];
     for (int64_t q = qa + tid; q < qb; q += 256) {
       const int pos = P.amap_pos[q];
       const int j = pos / m, i = pos - j * m;
@@ -308,6 +323,13 @@ __global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t
       for (int i = max(i0, j) + lane; i < ie; i += 32) cbp[(i - w) + (size_t)(j - w) * r] = src[i];
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_assemble_large(PlanDev P, const int32_t* __restrict__ items, int nitems) {
+  const int b = blockIdx.x;
+  if (b >= nitems) return;
+  __shared__ double T[ASM_TILE];
+  assemble_tile_body(P, items + 8 * (size_t)b, T);
 }
 
 // CTA-level pivot-free LDL^T of an nb x nb block (nb <= NB = 64) held column-major in shared
@@ -873,6 +895,26 @@ __device__ __forceinline__ void dag_raise(int* f) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
 #endif
 }
+// counters (extend-add tasks done per 64-column group of a front, contribution-block tiles done per
+// front, children done per front): a waiter needs every increment's writes, hence fence - add - fence
+__device__ __forceinline__ void dag_wait_count(const int* c, int expect) {
+#ifdef B2_EMULATE
+  if (*c < expect) { fprintf(stderr, "k_front_dag: wait on a counter that is not complete (%d < %d)\n", *c, expect); abort(); }
+#else
+  while (dag_peek_relaxed(c) < expect) __nanosleep(64);
+  (void)dag_peek(c);
+#endif
+}
+__device__ __forceinline__ int dag_count_up(int* c) {
+#ifdef B2_EMULATE
+  return (*c)++;
+#else
+  __threadfence();
+  const int old = atomicAdd(c, 1);
+  __threadfence();
+  return old;
+#endif
+}
 // operands written by other CTAs of the same launch: read through L2
 __device__ __forceinline__ double dag_ld(const double* p) {
 #ifdef B2_EMULATE
@@ -888,6 +930,58 @@ __device__ __forceinline__ double frag_c2a(double c0, double c1, int h, int lane
   return (lane & 1) ? v1 : v0;
 }
 
+// Extend-add of ONE NB x NB tile of a front in shared memory: Ts[col * DAG_LDT + row].  The host lists,
+// per tile, the children whose contribution block lands on it with the ranges of child rows / child
+// columns that fall into the tile's row / column block (tl_ptr / tl_ent: child descriptor, ia, iz, ja,
+// jz), children ascending; per 64-column block of the front the range of its A entries (ta_ptr).
+constexpr int DAG_DESC = 32;                     // child descriptors staged per round
+__device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int s, int m, int i0, int iend, int j0,
+                                                  int tgid, int agid, double* Ts, long long* sdesc) {
+  constexpr int LDT = DAG_LDT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < NB * LDT; idx += 256) Ts[idx] = 0.0;
+  const int e0 = P.tl_ptr[tgid], e1 = P.tl_ptr[tgid + 1];
+  __syncthreads();
+  {
+    const int64_t a0 = P.amap_ptr[s];
+    const int64_t qa = a0 + P.ta_ptr[agid], qb = a0 + P.ta_ptr[agid + 1];
+    for (int64_t q = qa + tid; q < qb; q += 256) {
+      const int pos = P.amap_pos[q];
+      const int j = pos / m, i = pos - j * m;
+      if (i >= i0 && i < iend) Ts[(j - j0) * LDT + (i - i0)] = P.nzval[P.amap_slot[q]];
+    }
+  }
+  for (int eb = e0; eb < e1; eb += DAG_DESC) {
+    const int cnt = min(DAG_DESC, e1 - eb);
+    __syncthreads();                             // A entries placed / previous round consumed
+    if (tid < cnt) {
+      // descriptor of child eb + tid: offsets of its rel[] and of its contribution block, its order
+      const int32_t* d = P.tl_ent + 6 * (size_t)(eb + tid);
+      const int ce = d[0];
+      sdesc[4 * tid] = P.asm_off[2 * ce];
+      sdesc[4 * tid + 1] = P.asm_off[2 * ce + 1];
+      sdesc[4 * tid + 2] = ((long long)d[1] << 32) | (unsigned)d[2];
+      sdesc[4 * tid + 3] = ((long long)P.asm_rc[ce] << 48) | ((long long)d[3] << 24) | (long long)d[4];
+    }
+    __syncthreads();
+    for (int k = 0; k < cnt; k++) {
+      const int32_t* relc = P.rel + sdesc[4 * k];
+      const double* cb = P.CB + sdesc[4 * k + 1];
+      const int ia = (int)(sdesc[4 * k + 2] >> 32), iz = (int)(sdesc[4 * k + 2] & 0xffffffffll);
+      const int rc = (int)(sdesc[4 * k + 3] >> 48), ja = (int)((sdesc[4 * k + 3] >> 24) & 0xffffff), jz = (int)(sdesc[4 * k + 3] & 0xffffff);
+      // warp <-> child column, lanes over the child rows of the tile's row block (contiguous in the
+      // child's contribution block); within one child every entry has its own destination
+      for (int j = ja + warp; j < jz; j += 8) {
+        double* dst = Ts + (relc[j] - j0) * LDT - i0;
+        const double* src = cb + (size_t)j * rc;
+        for (int i = max(ia, j) + lane; i < iz; i += 32) dst[relc[i]] += src[i];
+      }
+      __syncthreads();                           // the next child may land on the same entries
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* __restrict__ items, int ntasks,
                                                       int* __restrict__ tflag, int* __restrict__ ticket, int trace_base) {
   constexpr int KC = UPD_KC, LDT = DAG_LDT, LDL = DAG_LDL;
@@ -899,6 +993,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
   double* Mi = Lr + NB * LDL;                    // inverses of the 8 x 8 diagonal blocks of L(J,J), row-major
   double* rdv = Mi + 8 * 64;                     // 1 / d of the pivot block
   __shared__ int s_tk;
+  __shared__ long long sdesc[4 * DAG_DESC];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp & 1, wc = warp >> 1;       // warp tile of the update: rows wr*32.., cols wc*16..
@@ -909,11 +1004,17 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
     __syncthreads();
     const int tk = s_tk;
     if (tk >= ntasks) break;
-    const int s = items[4 * tk], I = items[4 * tk + 1], fb = items[4 * tk + 3];
-    const int J = items[4 * tk + 2] & 0xffff;
-    const int kind = items[4 * tk + 2] >> 16;
+    const int32_t* it = items + 8 * (size_t)tk;
+    const int s = it[0], I = it[1], fb = it[3];
+    const int J = it[2] & 0xffff;
+    const int kind = it[2] >> 16;
     const bool chain = kind == 1;                // I == J >= 1: tiles (J, J-1) and (J, J)
     const bool ypre = kind == 2;                 // I == J >= 2: tile (J, J) up to date with the pivot blocks p < J-1
+    // task = (front, I, J | kind << 16, first flag, first tile list, first A range, -, front record);
+    // per-front record: [0] -, [1] tiles of its contribution block, [2] parent's record (-1: none in
+    // this launch), [3] children in this launch
+    const int df = it[7];
+    const int32_t* fr = P.dfr + 4 * (size_t)df;
 #ifdef B2_TIMING
     if (tid == 0 && trace_base + tk < DAG_TRACE_MAX) {
       unsigned smid;
@@ -931,6 +1032,12 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
     const bool pivcol = J < np;
     double* Lp = P.Lx + P.lptr[s];
     double acc[4][2][2];
+    // the children factored by THIS launch (the others are complete: earlier launches) hand their
+    // contribution blocks over through a counter of the front
+    if (fr[3] > 0) {
+      if (tid == 0) dag_wait_count(P.dcnt + P.dcnt_ch + df, fr[3]);
+      __syncthreads();
+    }
     // ---- the update(s): one tile, or (J, J-1) then (J, J) of a chain task ------------------
     for (int ph = 0; ph < (chain ? 2 : 1); ph++) {
       const int Jt = (chain && ph == 0) ? J - 1 : J;            // column block of this tile
@@ -948,20 +1055,36 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
       for (int a = 0; a < 4; a++)
         B2_UNROLL
         for (int c = 0; c < 2; c++) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
-      // the tile as the extend-add left it (a previous launch): read now, used after the K loop
+      // the tile before any update: the extend-add happens HERE, in shared memory (As | Bs, free at
+      // this point) -- the A entries of the tile, then the children's contribution blocks one child
+      // after the other (fixed order, no atomics: deterministic sums) -- so an assembled front is never
+      // written to / read back from HBM; a chain task takes its diagonal tile from the ypre task
       double cold[4][2][2];
-      const double* Cb = pivcol ? Lp : (P.CB + P.cbptr[s]);
-      B2_UNROLL
-      for (int a = 0; a < 4; a++)
+      if (from_ypre) {
         B2_UNROLL
-        for (int cc = 0; cc < 2; cc++)
+        for (int a = 0; a < 4; a++)
           B2_UNROLL
-          for (int e = 0; e < 2; e++) {
-            const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
-            const bool ok = ri < iend && cj < jend && ri >= cj;
-            const double* src = pivcol ? (Cb + ri + (size_t)cj * m) : (Cb + (ri - w) + (size_t)(cj - w) * r);
-            cold[a][cc][e] = ok ? (from_ypre ? dag_ld(src) : *src) : 0.0;
-          }
+          for (int cc = 0; cc < 2; cc++)
+            B2_UNROLL
+            for (int e = 0; e < 2; e++) {
+              const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
+              const bool ok = ri < iend && cj < jend && ri >= cj;
+              cold[a][cc][e] = ok ? dag_ld(Lp + ri + (size_t)cj * m) : 0.0;
+            }
+      } else {
+        dag_assemble_tile(P, s, m, i0, iend, j0, it[4] + Jt * nrb + I, it[5] + Jt, As, sdesc);
+        B2_UNROLL
+        for (int a = 0; a < 4; a++)
+          B2_UNROLL
+          for (int cc = 0; cc < 2; cc++)
+            B2_UNROLL
+            for (int e = 0; e < 2; e++) {
+              const int li = wr * 32 + a * 8 + g, lj = wc * 16 + cc * 8 + 2 * t + e;
+              const bool ok = i0 + li < iend && j0 + lj < jend && i0 + li >= j0 + lj;
+              cold[a][cc][e] = ok ? As[lj * LDT + li] : 0.0;
+            }
+        __syncthreads();                         // As | Bs go back to the operand pipeline
+      }
       const int nchunk = (Ktot + KC - 1) / KC;
       if (nchunk > 0) {
         const int gi = i0 + lr, gj = j0 + lr;
@@ -1073,6 +1196,10 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
             const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
             if (ri < iend && cj < jend && ri >= cj) Cb[(ri - w) + (size_t)(cj - w) * r] = -acc[a][cc][e];
           }
+      // the last tile of the contribution block completes the front: tell the parent
+      __syncthreads();
+      if (tid == 0 && dag_count_up(P.dcnt + P.dcnt_cb + df) == fr[1] - 1 && fr[2] >= 0)
+        (void)dag_count_up(P.dcnt + P.dcnt_ch + fr[2]);
       DAG_TRACE(9);
       continue;
     }

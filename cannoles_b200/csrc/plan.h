@@ -34,6 +34,15 @@ struct PlanDev {
   const int32_t* ug_src;   //   of the child update entries (offsets into upd) that land on it, in child order
   const uint8_t* ug_row;   //   and the row of the front each entry lands on (fronts of order <= 255: the thread-per-front kernels)
   int* flags;  // [0] = breakdown (exact zero pivot seen)
+  // cross-level dataflow factorization (k_front_dag): per-front records (4 ints each, see the
+  // kernel) and the counters (zeroed with the tile flags before every factorization):
+  // contribution-block tiles done per front at dcnt_cb, children done per front at dcnt_ch
+  const int32_t* dfr;
+  int* dcnt;
+  int dcnt_cb, dcnt_ch;
+  const int32_t* tl_ptr;   // per tile of the dataflow fronts (first list + J * nrb + I): range in tl_ent
+  const int32_t* tl_ent;   // 6 ints: child descriptor (asm_rc / asm_off), child rows [ia, iz), child columns [ja, jz), -
+  const int32_t* ta_ptr;   // per 64-column block of the dataflow fronts: range of its A entries relative to amap_ptr[front]
 };
 
 constexpr int NB = 64;        // pivot block width of the tiled path (== TILE: tile (0,0) is the next diagonal block)

@@ -63,10 +63,13 @@ class B200Struct:
     ``refine_steps`` is the MAXIMUM number of iterative-refinement sweeps of ``solve_ldl``; a sweep
     is taken only while ||K d + rhs|| / ||rhs|| > ``refine_tol`` (north_star bar: 1e-12).
 
-    ``shift_retries=True`` uses the caller protocol of ``newton_system!``
+    ``shift_retries=True`` exploits the caller protocol of ``newton_system!``
     (reference/src/CaNNOLeS.jl:1023-1043): a call whose trailing rho segment is a non-zero
-    constant is a retry of the previous call with only that segment changed, so nothing is
-    re-uploaded and the diagonal is shifted on the device (bit-identical CSC values).
+    constant is *probably* a retry of the previous call with only that segment changed, so the
+    diagonal is shifted on the device and the factorization starts at once (bit-identical CSC
+    values) while the upload and a device-side comparison with the previous values run on a copy
+    stream; if anything else changed, the full factorization of the new values is what is returned
+    (``b2_factorize_retry``).  Correctness never depends on the caller following the protocol.
     """
 
     def __init__(self, N, rows, cols, vals, nvar=None, nequ=None, ncon=None, ordering=ORDER_ND,
@@ -151,17 +154,22 @@ class B200Struct:
         brk = C.c_int()
         n = len(vals)
         rho = vals[n - 1] if nvar > 0 else 0.0
-        is_retry = (self.shift_retries and self.n_upload > 0 and nvar > 0 and rho != 0.0
-                    and vals[n - nvar] == rho and vals is self.vals)
-        if is_retry:
-            rc = self._lib.b2_refactorize_shift(self._h, float(rho), math.nan, float(eig_tol),
-                                                C.byref(npos), C.byref(nzero), C.byref(nneg),
-                                                C.byref(brk))
-            if rc == 0:
+        # A call that LOOKS like a rho retry of newton_system! (trailing segment a non-zero constant,
+        # reference/src/CaNNOLeS.jl:1029-1043) goes through b2_factorize_retry: the shifted matrix is
+        # factorized speculatively while the device checks that nothing else changed since the last
+        # upload -- a caller that also edited H/J gets the full factorization of what it passed.
+        looks_like_retry = (self.shift_retries and self.n_upload > 0 and nvar > 0 and rho != 0.0
+                            and vals[n - nvar] == rho)
+        if looks_like_retry:
+            held = C.c_int()
+            self._check(self._lib.b2_factorize_retry(self._h, _pd(vals), float(rho), float(eig_tol),
+                                                     C.byref(npos), C.byref(nzero), C.byref(nneg),
+                                                     C.byref(brk), C.byref(held)))
+            if held.value:
                 self.n_shift += 1
             else:
-                is_retry = False
-        if not is_retry:
+                self.n_upload += 1
+        else:
             self._check(self._lib.b2_factorize(self._h, _pd(vals), float(eig_tol), C.byref(npos),
                                                C.byref(nzero), C.byref(nneg), C.byref(brk)))
             self.n_upload += 1

@@ -86,6 +86,16 @@ int b2_factorize(b2_handle* h, const double* vals, double eig_tol, int64_t* npos
 int b2_refactorize_shift(b2_handle* h, double rho, double delta_or_nan, double eig_tol,
                          int64_t* npos, int64_t* nzero, int64_t* nneg, int* breakdown);
 
+/* try_to_factorize as newton_system! re-enters it for a rho retry (src/CaNNOLeS.jl:1032, :1039: the
+ * same vals buffer with only the trailing rho segment rewritten).  SAME RESULT as
+ * b2_factorize(h, vals, ...) bit for bit, whatever the caller did to vals: the matrix shifted by
+ * `rho` on the device is factorized at once while vals is uploaded on a copy stream and compared
+ * on the device with the previous upload; if anything but the rho segment changed (or the segment
+ * is not the constant `rho`) the factorization is redone from the fresh upload.
+ * *speculation_held (may be NULL) = 1 if the shifted factorization was the answer. */
+int b2_factorize_retry(b2_handle* h, const double* vals, double rho, double eig_tol, int64_t* npos,
+                       int64_t* nzero, int64_t* nneg, int* breakdown, int* speculation_held);
+
 /* solve_ldl!: d_out = (negate ? -1 : +1) * K^{-1} rhs with the last factorization.
  * refine_steps >= 0 iterative-refinement sweeps with the assembled K; if relres != NULL it
  * receives ||K x - rhs||_2 / ||rhs||_2 of the returned (un-negated) solution. */

@@ -6,8 +6,10 @@
 # (MA57Struct :17-43, LDLFactStruct :45-98) and is `include`d from src/CaNNOLeS.jl next to
 # `include("solver_types.jl")`.  The two edits to src/CaNNOLeS.jl are listed in INTEGRATION.md.
 #
-# Limitation (state it in the docstring at src/CaNNOLeS.jl:121): Float64 only; the reference's
-# LDLFactorizations path is generic in T (test/runtests.jl:102-113 exercises Float16..BigFloat).
+# Limitation (state it in the docstring at src/CaNNOLeS.jl:121): the device path is Float64 only.
+# The reference's LDLFactorizations path is generic in T (test/runtests.jl:102-113 exercises
+# Float16..BigFloat): for any other element type the constructor below warns and hands back an
+# `LDLFactStruct`, exactly as src/CaNNOLeS.jl:317-320 downgrades `:ma57` when HSL is missing.
 
 const libb200 = get(ENV, "CANNOLES_B200_LIB", "libcannoles_b200")
 
@@ -17,18 +19,48 @@ const B2_ORDER_AMD = Cint(3)
 b200_error() = unsafe_string(ccall((:b2_last_error, libb200), Cstring, ()))
 b200_check(rc::Cint) = rc == 0 ? nothing : error("libcannoles_b200: " * b200_error())
 
-"""Opaque device factor; what `LDLT.factor` is for this backend (read at src/CaNNOLeS.jl:1049)."""
+"""
+Opaque device factor; what `LDLT.factor` is for this backend (read at src/CaNNOLeS.jl:1049).
+
+It OWNS a reference to every host buffer it has pinned with `b2_register_host` (`vals`, and `rhs` /
+`d` from the first `solve_ldl!` on), so that the garbage collector cannot free a still-registered
+buffer before the finalizer has unregistered it (`b2_free` unregisters, then releases the device).
+"""
 mutable struct B200Factor
   handle::Ptr{Cvoid}
   refine_steps::Cint
+  pinned::Vector{Vector{Float64}}     # buffers registered with the CUDA driver: kept alive here
   function B200Factor(handle, refine_steps)
-    F = new(handle, refine_steps)
-    finalizer(F) do f
-      f.handle == C_NULL || ccall((:b2_free, libb200), Cint, (Ptr{Cvoid},), f.handle)
-      f.handle = C_NULL
-    end
+    F = new(handle, refine_steps, Vector{Float64}[])
+    finalizer(close!, F)
     return F
   end
+end
+
+"""Release the device factor and unpin the host buffers now (idempotent; also the finalizer)."""
+function close!(F::B200Factor)
+  if F.handle != C_NULL
+    ccall((:b2_free, libb200), Cint, (Ptr{Cvoid},), F.handle)   # unregisters what it registered
+    F.handle = C_NULL
+  end
+  empty!(F.pinned)
+  return nothing
+end
+
+# pin a caller-owned buffer once (addresses are stable: src/CaNNOLeS.jl:241-243, 276-279); a failed
+# registration only costs PCIe speed (pageable copies), so it is reported, not fatal
+function b200_pin!(F::B200Factor, buf::Vector{Float64})
+  for b in F.pinned
+    b === buf && return true
+  end
+  rc = ccall((:b2_register_host, libb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+             F.handle, buf, sizeof(buf))
+  if rc == 0
+    push!(F.pinned, buf)
+    return true
+  end
+  @warn "libcannoles_b200: could not pin a host buffer, copies will be pageable" error = b200_error()
+  return false
 end
 
 mutable struct B200Struct <: LinearSolverStruct
@@ -39,8 +71,15 @@ mutable struct B200Struct <: LinearSolverStruct
   ordering::Cint
   device::Cint
   factor::B200Factor             # handle == C_NULL until the first try_to_factorize
-  nuploads::Int                  # to recognise the rho retries of newton_system!
+  nuploads::Int                  # full uploads so far
+  nshifts::Int                   # rho retries answered by the device-side shift
   inertia::NTuple{3, Int64}
+  # out-parameters of the ccalls, allocated once (allocation test, test/runtests.jl:28-36)
+  npos::Base.RefValue{Int64}
+  nzero::Base.RefValue{Int64}
+  nneg::Base.RefValue{Int64}
+  brk::Base.RefValue{Cint}
+  held::Base.RefValue{Cint}
 end
 
 # ctor with the reference's signature X(N, rows, cols, vals) (src/solver_types.jl:21, :61).
@@ -48,7 +87,15 @@ end
 # try_to_factorize), so the symbolic analysis is done lazily at the first factorization.
 function B200Struct(N, rows::Vector{Int64}, cols::Vector{Int64}, vals::Vector{Float64};
                     ordering = B2_ORDER_ND, device = 0, refine_steps = 1)
-  return B200Struct(rows, cols, vals, N, ordering, device, B200Factor(C_NULL, refine_steps), 0, (0, 0, 0))
+  return B200Struct(rows, cols, vals, N, ordering, device, B200Factor(C_NULL, refine_steps), 0, 0,
+                    (0, 0, 0), Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0), Ref{Cint}(0))
+end
+
+# Any other element type: the device path is Float64 only -- warn and fall through to the generic
+# LDLFactorizations adapter, like the HSL guard of src/CaNNOLeS.jl:317-320 does for :ma57.
+function B200Struct(N, rows::Vector{Ti}, cols::Vector{Ti}, vals::Vector{T}; kwargs...) where {T, Ti <: Integer}
+  @warn "linsolve = :b200 is Float64 / Int64 only; using :ldlfactorizations for eltype $T / $Ti"
+  return LDLFactStruct(N, rows, cols, vals)
 end
 
 get_vals(LDLT::B200Struct) = LDLT.vals          # src/solver_types.jl:25, :67
@@ -60,9 +107,9 @@ function b200_analyze!(LDLT::B200Struct, nvar, nequ, ncon)
     LDLT.N, length(LDLT.vals), LDLT.rows, LDLT.cols, nvar, nequ, ncon, LDLT.ordering, C_NULL,
     LDLT.device, h))
   LDLT.factor.handle = h[]
-  # vals has a stable address for the life of the solver (src/CaNNOLeS.jl:276-279): pin it once
-  ccall((:b2_register_host, libb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
-        h[], LDLT.vals, sizeof(LDLT.vals))
+  # vals has a stable address for the life of the solver (src/CaNNOLeS.jl:276-279): pin it once;
+  # the factor keeps it alive until it has been unregistered
+  b200_pin!(LDLT.factor, LDLT.vals)
   return LDLT
 end
 
@@ -71,29 +118,33 @@ function try_to_factorize(LDLT::B200Struct, vals::AbstractVector{Float64}, nvar:
                           nequ::Integer, ncon::Integer, eig_tol::Float64)
   LDLT.factor.handle == C_NULL && b200_analyze!(LDLT, nvar, nequ, ncon)
   h = LDLT.factor.handle
-  npos, nzero, nneg, brk = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0)
   ρ = nvar > 0 ? vals[end] : 0.0
-  # newton_system! (src/CaNNOLeS.jl:1029-1043) re-enters with ONLY the trailing rho segment
-  # changed to a non-zero constant: shift the diagonal on the device, upload nothing.
-  retry = LDLT.nuploads > 0 && nvar > 0 && ρ != 0 && vals === LDLT.vals && vals[end - nvar + 1] == ρ
-  rc = Cint(-1)
-  if retry
-    rc = ccall((:b2_refactorize_shift, libb200), Cint,
-      (Ptr{Cvoid}, Float64, Float64, Float64, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cint}),
-      h, ρ, NaN, eig_tol, npos, nzero, nneg, brk)
-  end
-  if rc != 0
+  # newton_system! (src/CaNNOLeS.jl:1029-1043) re-enters with ONLY the trailing rho segment changed
+  # to a non-zero constant.  A call that looks like that goes through b2_factorize_retry: the matrix
+  # shifted on the device is factorized at once while vals is uploaded on a copy stream and compared
+  # with the previous upload on the device; if the caller changed anything else the result is the
+  # full factorization of what it passed -- never a stale one.
+  looks_like_retry = LDLT.nuploads > 0 && nvar > 0 && ρ != 0 && vals[end - nvar + 1] == ρ
+  if looks_like_retry
+    b200_check(ccall((:b2_factorize_retry, libb200), Cint,
+      (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cint}, Ref{Cint}),
+      h, vals, ρ, eig_tol, LDLT.npos, LDLT.nzero, LDLT.nneg, LDLT.brk, LDLT.held))
+    LDLT.held[] != 0 ? (LDLT.nshifts += 1) : (LDLT.nuploads += 1)
+  else
     b200_check(ccall((:b2_factorize, libb200), Cint,
       (Ptr{Cvoid}, Ptr{Float64}, Float64, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cint}),
-      h, vals, eig_tol, npos, nzero, nneg, brk))
+      h, vals, eig_tol, LDLT.npos, LDLT.nzero, LDLT.nneg, LDLT.brk))
     LDLT.nuploads += 1
   end
-  LDLT.inertia = (npos[], nzero[], nneg[])
-  return npos[] == nvar && nzero[] == 0           # src/solver_types.jl:96
+  LDLT.inertia = (LDLT.npos[], LDLT.nzero[], LDLT.nneg[])
+  return LDLT.npos[] == nvar && LDLT.nzero[] == 0           # src/solver_types.jl:96
 end
 
 # solve_ldl! (src/solver_types.jl:26, :69): d = -(K \ rhs); returns true like both reference backends.
-function solve_ldl!(rhs::AbstractVector{Float64}, factor::B200Factor, d::AbstractVector{Float64})
+# rhs and d are allocated once by the solver (src/CaNNOLeS.jl:241-243): pinned at the first call.
+function solve_ldl!(rhs::Vector{Float64}, factor::B200Factor, d::Vector{Float64})
+  b200_pin!(factor, rhs)
+  b200_pin!(factor, d)
   b200_check(ccall((:b2_solve, libb200), Cint,
     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ptr{Float64}),
     factor.handle, rhs, d, 1, factor.refine_steps, C_NULL))

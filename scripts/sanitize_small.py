@@ -16,8 +16,8 @@ from cannoles_b200.workloads import dense_batch_systems, first_system, make_conf
 EPS = 2.0 ** -52
 # the last case has fronts with three pivot blocks and runs every tiled front through the dataflow
 # kernel (k_front_dag: plain, chain and ypre tasks); the first two take the k_trsm / k_update chain
-for cfg, size, dag_min_np in (("c4", 14, "99"), ("c2", 300, "99"), ("c4", 60, "1")):
-    os.environ["B2_DAG_MIN_NP"] = dag_min_np
+for cfg, size, dag_min_np in (("c4", 14, "0"), ("c2", 300, "0"), ("c4", 60, "1000000000"), ("c4", 60, "40")):
+    os.environ["B2_DAG_LEVEL_MAX"] = dag_min_np   # 0: launch chain only; huge: every front through k_front_dag; 40: the top levels
     nls, method, _ = make_config(cfg, size)
     ctor = functools.partial(B200Struct, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon, refine_steps=1,
                              refine_tol=0.0, shift_retries=True)
@@ -29,7 +29,7 @@ for cfg, size, dag_min_np in (("c4", 14, "99"), ("c2", 300, "99"), ("c4", 60, "1
     d = np.zeros(B.N)
     B.solve_ldl(rhs, d)
     st = B.stats()
-    print(cfg, size, "N", B.N, "ok", ok, ok2, "relres", B.last_relres, "n_large", st["n_large"], "max_front", st["max_front"], "max_width", st["max_width"], "dag_min_np", dag_min_np)
+    print(cfg, size, "N", B.N, "ok", ok, ok2, "relres", B.last_relres, "n_large", st["n_large"], "max_front", st["max_front"], "max_width", st["max_width"], "dag_level_max", dag_min_np)
     B.close()
 nb = 3
 s, vals, rhs = dense_batch_systems(range(nb))

@@ -27,6 +27,8 @@ def check_against_oracle(ctor, oracle_cls, N, rows, cols, vals, nvar, nequ, ncon
     cp, rv = B.csc()
     assert np.array_equal(cp, O.colptr) and np.array_equal(rv, O.rowval)
     assert np.array_equal(B.nzval, O.nzval)
+    # symbolic: nnz(L) of the same elimination order (integer work: equal)
+    assert B.stats()["nnzL"] == O.nnzL
     # inertia bit-exact
     assert B.last_inertia[:3] == O.inertia(EPS)
     if not ok:
@@ -80,6 +82,38 @@ def check_shift_path(ctor, oracle_cls, N, rows, cols, vals, nvar, nequ, ncon, rh
     O = oracle_cls(N, rows, cols, vals, perm=B.perm)
     O.try_to_factorize(vals, nvar, nequ, ncon, EPS)
     assert np.array_equal(nz_shift, O.nzval)
+
+
+def check_retry_is_validated(ctor, oracle_cls, N, rows, cols, vals, nvar, nequ, ncon, rho, ordering=0):
+    """A caller that does NOT follow newton_system!'s protocol: it sets the rho segment to a non-zero
+    constant (looks like a retry) but also edits H / J.  The speculative shift must be discarded and
+    the result must be the factorization of what was passed, bit for bit."""
+    vals = vals.copy()
+    B = ctor(N, rows, cols, vals, nvar=nvar, nequ=nequ, ncon=ncon, ordering=ordering)
+    B.try_to_factorize(vals, nvar, nequ, ncon, EPS)
+    vals[-nvar:] = rho
+    vals[: len(vals) // 3] *= 1.25                     # LM-style caller: other segments change too
+    B.try_to_factorize(vals, nvar, nequ, ncon, EPS)
+    assert B.n_shift == 0 and B.n_upload == 2          # speculation rejected, full factorization returned
+    C = ctor(N, rows, cols, vals, nvar=nvar, nequ=nequ, ncon=ncon, ordering=ordering, shift_retries=False)
+    C.try_to_factorize(vals, nvar, nequ, ncon, EPS)
+    assert np.array_equal(B.nzval, C.nzval) and np.array_equal(B.factor.d, C.factor.d)
+    assert B.last_inertia == C.last_inertia
+    O = oracle_cls(N, rows, cols, vals, perm=B.perm)
+    O.try_to_factorize(vals, nvar, nequ, ncon, EPS)
+    assert np.array_equal(B.nzval, O.nzval)
+    # a non-constant trailing segment whose ends happen to agree is not a retry either
+    vals[-nvar:] = rho * 2
+    vals[-nvar + 1] = rho * 3
+    B.try_to_factorize(vals, nvar, nequ, ncon, EPS)
+    C.try_to_factorize(vals, nvar, nequ, ncon, EPS)
+    assert np.array_equal(B.nzval, C.nzval) and np.array_equal(B.factor.d, C.factor.d)
+    # and a genuine retry after all that is taken by the shift path again
+    vals[-nvar:] = rho * 4
+    B.try_to_factorize(vals, nvar, nequ, ncon, EPS)
+    C.try_to_factorize(vals, nvar, nequ, ncon, EPS)
+    assert B.n_shift == 1
+    assert np.array_equal(B.nzval, C.nzval) and np.array_equal(B.factor.d, C.factor.d)
 
 
 def run_cannoles_both(nls, ctor, method="Newton", **kw):

@@ -16,6 +16,18 @@ from oracle import LDLFactStruct  # noqa: E402
 from tests.problems import EPS, dense_from_coo, random_kkt  # noqa: E402
 
 
+def write_ref_input(name, N, rows, cols, vals, nvar, nequ, ncon, rhs):
+    """The same inputs as plain text for oracle/gen_ref_vectors.jl (Julia stdlib only): line 1
+    `N nnz nvar nequ ncon`, nnz lines `row col val` (1-based), N lines rhs."""
+    os.makedirs(os.path.join(HERE, "ref_inputs"), exist_ok=True)
+    with open(os.path.join(HERE, "ref_inputs", name + ".txt"), "w") as f:
+        f.write(f"{N} {len(vals)} {nvar} {nequ} {ncon}\n")
+        for r, c, v in zip(rows, cols, vals):
+            f.write(f"{int(r)} {int(c)} {float(v):.17g}\n")
+        for v in rhs:
+            f.write(f"{float(v):.17g}\n")
+
+
 def one(name, N, rows, cols, vals, nvar, nequ, ncon, perm=None):
     L = LDLFactStruct(N, rows, cols, vals, perm=perm)
     ok = L.try_to_factorize(vals, nvar, nequ, ncon, EPS)
@@ -27,6 +39,7 @@ def one(name, N, rows, cols, vals, nvar, nequ, ncon, perm=None):
         assert np.allclose(d, -np.linalg.solve(K, rhs), rtol=1e-9, atol=1e-11)
         ev = np.linalg.eigvalsh(K)
         assert L.inertia(EPS) == (int((ev > 0).sum()), 0, int((ev < 0).sum()))
+    write_ref_input(name, N, rows, cols, vals, nvar, nequ, ncon, rhs)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), N=N, rows=rows, cols=cols, vals=vals,
                         dims=np.array([nvar, nequ, ncon]), perm=L.perm, colptr=L.colptr,
                         rowval=L.rowval, nzval=L.nzval, D=L.factor.d, inertia=np.array(L.inertia(EPS)),

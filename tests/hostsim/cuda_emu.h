@@ -249,6 +249,8 @@ template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; retu
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
 inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
+inline long long __double_as_longlong(double a) { long long o; memcpy(&o, &a, 8); return o; }
+inline double __longlong_as_double(long long a) { double o; memcpy(&o, &a, 8); return o; }
 inline double __drcp_rn(double a) { return 1.0 / a; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline double __dmul_rn(double a, double b) { return a * b; }

@@ -29,10 +29,27 @@ def test_small_front_path(ctor, oracle_cls, ordering, monkeypatch):
 def test_tiled_front_path(ctor, oracle_cls, ordering, monkeypatch, dag):
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")     # force every front of order > 8 onto the tiled path
     monkeypatch.setenv("B2_DAG", dag)             # dataflow kernel (k_front_dag) / k_trsm + k_update launch chain
-    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", "1000000000")
     N, r, c, v = random_kkt(50, 60, 15, 0.3, 22)
     B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 50, 60, 15, ordering=ordering)
     assert B.stats()["n_large"] > 0
+
+
+@pytest.mark.parametrize("level_max", ["2", "6", "40"])
+def test_cross_level_dataflow_over_the_top_of_the_tree(ctor, oracle_cls, monkeypatch, level_max):
+    """The top levels of the assembly tree (those with at most `level_max` fronts) in ONE k_front_dag
+    launch -- extend-add tasks, children counters, small fronts cut into tiles like the others --
+    below them the per-level launches (small fronts in shared memory, k_trsm / k_update chain)."""
+    from cannoles_b200.workloads import first_system
+    import functools
+    monkeypatch.setenv("B2_SMALL_MAX_M", "24")
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", level_max)
+    nls = PoissonParamEst(20)
+    s, rhs = first_system(nls, "Newton", functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon))
+    B, _ = ec.check_against_oracle(ctor, oracle_cls, s.LDLT.N, s.rows, s.cols, s.vals, nls.nvar, nls.nequ, nls.ncon,
+                                   same_perm_tol=1e-8)
+    st = B.stats()
+    assert st["n_large"] > 0 and st["launches_factor"] < 40
 
 
 @pytest.mark.parametrize("dag", ["1", "0"])
@@ -41,7 +58,7 @@ def test_tiled_path_multi_block_front(ctor, oracle_cls, monkeypatch, dag):
     with the dataflow kernel: a plain diagonal task, two chain tasks and one ypre task."""
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")
     monkeypatch.setenv("B2_DAG", dag)
-    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", "1000000000")
     N, r, c, v = random_kkt(60, 70, 20, 0.5, 71)
     B, _ = ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 60, 70, 20, ordering=1)
     assert B.stats()["max_width"] > 128
@@ -52,7 +69,7 @@ def test_dataflow_kernel_tile_boundaries(ctor, oracle_cls, monkeypatch, N):
     """One dense root front of order N through k_front_dag: full and partial last pivot blocks (N a
     multiple of 64, one more, one less), one to four pivot blocks (plain, chain and ypre tasks)."""
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")
-    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", "1000000000")
     nv = N // 3
     ne = N // 2
     nc = N - nv - ne
@@ -66,7 +83,7 @@ def test_dataflow_kernel_zero_pivot_is_reported_and_does_not_hang(ctor, monkeypa
     """An exact zero as the very first pivot of a 193-order front in k_front_dag: the breakdown flag
     comes back, every tile flag is still raised (the tasks behind it run on NaNs instead of waiting)."""
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")
-    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", "1000000000")
     nv, ne, nc = 64, 96, 33
     N, r, c, v = random_kkt(nv, ne, nc, 0.9, 293)
     v = v.copy()
@@ -83,7 +100,7 @@ def test_tiled_path_multi_chunk_trsm(ctor, oracle_cls, monkeypatch, dag):
     (launch chain); five row blocks with a contribution block (dataflow kernel)."""
     monkeypatch.setenv("B2_SMALL_MAX_M", "8")
     monkeypatch.setenv("B2_DAG", dag)
-    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", "1000000000")
     N, r, c, v = random_kkt(100, 130, 30, 0.5, 73)
     ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, 100, 130, 30, ordering=1)
 
@@ -153,6 +170,11 @@ def test_zero_pivot_is_reported_not_raised(ctor, oracle_cls):
     vals[-2:] = EPS ** (1 / 3)                    # the rho_0 retry of newton_system!
     assert B.try_to_factorize(vals, 2, 2, 1, EPS) is True
     assert B.n_shift == 1
+
+
+def test_retry_speculation_is_validated(ctor, oracle_cls):
+    N, r, c, v = random_kkt(30, 35, 9, 0.2, 27)
+    ec.check_retry_is_validated(ctor, oracle_cls, N, r, c, v, 30, 35, 9, rho=6.0554544523933395e-06)
 
 
 def test_shift_retry_is_bit_identical(ctor, oracle_cls):

@@ -50,6 +50,31 @@ def test_config5_instances_against_oracle(gpu_lib, oracle_cls):
     Bt.close()
 
 
+def test_config5_full_batch_inertia_against_oracle(gpu_lib, oracle_cls):
+    """BASELINE config 5 at its full size: all 8192 instances, the inertia triple of each equal to the
+    oracle's on the same elimination order (reference/src/solver_types.jl:90-96), and the step of every
+    16th instance within 1e-9."""
+    from cannoles_b200.batched import B200BatchStruct
+    from cannoles_b200.workloads import dense_batch_systems
+    nb = 8192
+    s, vals, rhs = dense_batch_systems(range(nb))
+    nv, ne, nc = s.nvar, s.nequ, s.ncon
+    N = nv + ne + nc
+    Bt = B200BatchStruct(N, s.rows, s.cols, nb, nv, ne, nc)
+    d = np.zeros((nb, N))
+    ok = Bt.factor_solve(vals, rhs, d)
+    O = oracle_cls(N, s.rows, s.cols, vals[0].copy(), perm=Bt.perm)
+    for b in range(nb):
+        ok_o = O.try_to_factorize(vals[b], nv, ne, nc, EPS)
+        assert bool(ok[b]) == ok_o
+        assert (Bt.npos[b], Bt.nzero[b], Bt.nneg[b]) == O.inertia(EPS)
+        if ok_o and b % 16 == 0:
+            xo = np.zeros(N)
+            O.solve_ldl(rhs[b], xo)
+            assert np.linalg.norm(d[b] - xo) <= 1e-9 * np.linalg.norm(xo)
+    Bt.close()
+
+
 def test_full_batch_properties(gpu_lib):
     """A large batch (2048 instances): expected inertia everywhere, residual through linearity
     (solve(2 rhs) == 2 solve(rhs) on the stored factors), masks respected."""

@@ -34,7 +34,7 @@ def test_golden_vectors(ctor):
 @pytest.mark.parametrize("ordering", [0, 1, 3])
 @pytest.mark.parametrize("seed", [31, 32])
 def test_random_kkt_against_oracle(ctor, oracle_cls, ordering, seed, monkeypatch):
-    monkeypatch.setenv("B2_DAG_MIN_NP", "1")     # every tiled front through k_front_dag, one-block fronts too
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", "1000000000")     # every tiled front through k_front_dag, one-block fronts too
     nv, ne, nc = 300, 400, 80
     N, r, c, v = random_kkt(nv, ne, nc, 0.02, seed)
     ec.check_against_oracle(ctor, oracle_cls, N, r, c, v, nv, ne, nc, ordering=ordering)
@@ -55,7 +55,7 @@ def test_dense_front_tiled_path_against_oracle(ctor, oracle_cls, monkeypatch, da
 def test_dataflow_kernel_tile_boundaries(ctor, oracle_cls, monkeypatch, N):
     """One dense root front of order N through k_front_dag: full and partial last pivot blocks,
     one to five pivot blocks (plain, chain and ypre tasks)."""
-    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", "1000000000")
     nv = N // 3
     ne = N // 2
     nc = N - nv - ne
@@ -69,7 +69,7 @@ def test_dataflow_kernel_tile_boundaries(ctor, oracle_cls, monkeypatch, N):
 def test_dataflow_kernel_zero_pivot_is_reported_and_does_not_hang(ctor, monkeypatch):
     """An exact zero as the very first pivot of a 193-order front in k_front_dag: the breakdown flag
     comes back, every tile flag is still raised (the tasks behind it run on NaNs instead of waiting)."""
-    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    monkeypatch.setenv("B2_DAG_LEVEL_MAX", "1000000000")
     nv, ne, nc = 64, 96, 33
     N, r, c, v = random_kkt(nv, ne, nc, 0.9, 293)
     v = v.copy()
@@ -108,6 +108,11 @@ def test_shift_retry_is_bit_identical(ctor, oracle_cls):
     ec.check_shift_path(ctor, oracle_cls, N, r, c, v, 200, 260, 50, rho=6.0554544523933395e-06)
 
 
+def test_retry_speculation_is_validated_on_the_device(ctor, oracle_cls):
+    N, r, c, v = random_kkt(200, 260, 50, 0.03, 36)
+    ec.check_retry_is_validated(ctor, oracle_cls, N, r, c, v, 200, 260, 50, rho=6.0554544523933395e-06)
+
+
 def test_config_slices_against_oracle(ctor, oracle_cls):
     from scripts.gpu_check import first_system
     for nls, method in ((ExtRosenbrockLinEq(20_000), "Newton_noFHess"), (PoissonParamEst(96), "Newton")):
@@ -140,15 +145,16 @@ def test_cannoles_on_a_config_slice_matches_oracle(ctor):
 
 
 @pytest.mark.parametrize("cfg", ["c2", "c4"])
-def test_full_size_properties(ctor, cfg):
-    """BASELINE.json full sizes: expected inertia (nvar, 0, nequ+ncon), residual <= 1e-12,
-    run-to-run determinism of the pivots, linearity of the solve."""
+def test_full_size_properties_and_oracle(ctor, oracle_cls, cfg):
+    """BASELINE.json full sizes with the BENCHED ordering (nested dissection): expected inertia
+    (nvar, 0, nequ+ncon), residual <= 1e-12, run-to-run determinism of the pivots, linearity of the
+    solve -- and the oracle run on the same elimination order: nnz(L) equal, inertia equal, pivots
+    within 1e-9, step within 1e-8 (reference/src/solver_types.jl:89-96, :69-77)."""
     from scripts.gpu_check import first_system
     nls, method = ((ExtRosenbrockLinEq(100_000), "Newton_noFHess") if cfg == "c2"
                    else (PoissonParamEst(512), "Newton"))
-    order = 0 if cfg == "c2" else 3
     s, rhs = first_system(nls, method, functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon,
-                                                         ordering=order, shift_retries=False))
+                                                         ordering=0, shift_retries=False))
     B, N = s.LDLT, s.LDLT.N
     assert B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
     assert B.last_inertia == (nls.nvar, 0, nls.nequ + nls.ncon, False)
@@ -162,6 +168,88 @@ def test_full_size_properties(ctor, cfg):
     B.solve_ldl(b2, x2)
     B.solve_ldl(2.5 * rhs + b2, x3)
     assert np.linalg.norm(x3 - (2.5 * x1 + x2)) <= 1e-9 * np.linalg.norm(x3)
+    # the oracle on the same elimination order
+    O = oracle_cls(N, s.rows, s.cols, s.vals, perm=B.perm)
+    assert O.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    assert B.stats()["nnzL"] == O.nnzL
+    assert np.array_equal(B.nzval, O.nzval)
+    assert B.last_inertia[:3] == O.inertia(EPS)
+    dO = O.factor.d
+    assert np.max(np.abs(d1 - dO) / np.abs(dO)) < 1e-9
+    xo = np.zeros(N)
+    O.solve_ldl(rhs, xo)
+    assert np.linalg.norm(x1 - xo) <= 1e-8 * np.linalg.norm(xo)
+    assert np.linalg.norm(O.matvec(x1) + rhs) <= ec.RESID_TOL * np.linalg.norm(rhs)
+
+
+def _rho_retry(B, s, nls):
+    """The caller protocol of newton_system! (reference/src/CaNNOLeS.jl:1023-1043): rho = 0, then rho0,
+    then x 100 while the inertia is wrong.  Returns (ok, rho, tries)."""
+    ok = B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    rho, tries = 0.0, 0
+    while not ok and tries < 6:
+        rho = EPS ** (1.0 / 3.0) if rho == 0.0 else 100.0 * rho
+        s.vals[len(s.vals) - nls.nvar:] = rho
+        ok = B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+        tries += 1
+    return ok, rho, tries
+
+
+@pytest.mark.timeout(900)
+def test_c3_full_size_properties(ctor):
+    """BASELINE config 3 at its full size (50 k cameras, 1 M points, N = 7 450 007, Gauss-Newton: zero
+    (1,1) block, so the rho = 0 attempt breaks down and the reference's rho0 retry is taken):
+    expected inertia, residual <= 1e-12, determinism, linearity."""
+    from cannoles_b200.workloads import first_system, make_config
+    nls, method, _ = make_config("c3", None)
+    s, rhs = first_system(nls, method, functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon,
+                                                         ordering=3, refine_steps=3, shift_retries=True))
+    B, N = s.LDLT, s.LDLT.N
+    assert N == 7_450_007
+    ok, rho, tries = _rho_retry(B, s, nls)
+    assert ok and B.last_inertia == (nls.nvar, 0, nls.nequ + nls.ncon, False)
+    assert tries >= 1 and B.n_shift == tries            # retries went through the device-side shift
+    d1 = B.factor.d
+    assert B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    assert np.array_equal(d1, B.factor.d)
+    x1, x2, x3 = np.zeros(N), np.zeros(N), np.zeros(N)
+    b2 = np.random.default_rng(9).standard_normal(N)
+    B.solve_ldl(rhs, x1)
+    assert B.last_relres <= ec.RESID_TOL
+    B.solve_ldl(b2, x2)
+    assert B.last_relres <= ec.RESID_TOL
+    B.solve_ldl(2.5 * rhs + b2, x3)
+    assert np.linalg.norm(x3 - (2.5 * x1 + x2)) <= 1e-7 * np.linalg.norm(x3)
+    B.close()
+
+
+@pytest.mark.parametrize("ordering", [0, 3])
+def test_c3_slice_against_oracle_with_rho_retry(ctor, oracle_cls, ordering):
+    """A 5000-camera slice of config 3 (N = 745 007, nnz(L) ~ 14 M): the rho = 0 breakdown, the rho0
+    retry, then the oracle on the same order: nnz(L), CSC values, inertia equal; pivots within 1e-7
+    (rho0 = 6e-6 on a zero (1,1) block: pivots span 1e-6 .. 1e+3), step within 1e-7."""
+    from cannoles_b200.workloads import first_system, make_config
+    nls, method, _ = make_config("c3", 5000)
+    s, rhs = first_system(nls, method, functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon,
+                                                         ordering=ordering, refine_steps=3))
+    B = s.LDLT
+    ok0 = B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    O = oracle_cls(B.N, s.rows, s.cols, s.vals, perm=B.perm)
+    assert O.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS) == ok0
+    assert B.stats()["nnzL"] == O.nnzL
+    ok, rho, tries = _rho_retry(B, s, nls) if not ok0 else (True, 0.0, 0)
+    assert ok and B.last_inertia == (nls.nvar, 0, nls.nequ + nls.ncon, False)
+    assert O.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    assert np.array_equal(B.nzval, O.nzval)
+    assert B.last_inertia[:3] == O.inertia(EPS)
+    dB, dO = B.factor.d, O.factor.d
+    assert np.max(np.abs(dB - dO) / np.abs(dO)) < 1e-7
+    d, do = np.zeros(B.N), np.zeros(B.N)
+    B.solve_ldl(rhs, d)
+    O.solve_ldl(rhs, do)
+    assert B.last_relres <= ec.RESID_TOL
+    assert np.linalg.norm(d - do) <= 1e-7 * np.linalg.norm(do)
+    B.close()
 
 
 def test_small_delta_needs_refinement_and_reaches_the_bar(ctor, oracle_cls):
