@@ -71,10 +71,17 @@ int Engine::build_plan() {
       any_large = front_m(S.level_sn[q]) > (int)small_max_m;
     if (any_large) dag_from_level = l;
   }
-  struct DagFront { int s, m, w, np, nrb; int32_t fb, df, tbase, abase; };
+  struct DagFront { int s, m, w, np, nrb; int32_t fb, df, tbase; };
   struct TlEnt { int64_t gid; int32_t ce, ia, iz, ja, jz; };
+  struct FlEnt { int64_t gid; int32_t dest, seq, isA, src; };
+  struct DTask { double key; int32_t rec[8]; };
+  std::vector<DTask> dtasks;                        // tasks of the dataflow launch with their schedule keys
+  std::vector<double> f_done, f_kdone;              // per front of the launch: modelled completion time / key of its last tile
+  std::vector<FlEnt> fl_tmp;                        // flat extend-add elements of the front in hand
+  std::vector<int32_t> fl_cnt, fl_ent;
+  const bool flat_ok = S.cb_store < (int64_t)INT32_MAX && S.nnzA < (int64_t)INT32_MAX;
   std::vector<TlEnt> tl_tmp;                        // (tile, child) pairs in front / child order
-  std::vector<int32_t> tl_cnt, ta_ptr;
+  std::vector<int32_t> tl_cnt;
   std::vector<DagFront> dagf;                       // fronts of the dataflow launch, in level order
   std::vector<int32_t> dag_of(S.nsuper, -1);        // front -> its record
   std::vector<int32_t> items_dag;                   // task records (8 ints each), level by level
@@ -249,7 +256,7 @@ int Engine::build_plan() {
         int w = front_w(s), m = front_m(s);
         int np = (w + NB - 1) / NB, nrb = np + (m - w + NB - 1) / NB;
         if (m >= 65536 || ntflag + (int64_t)np * (nrb + 1) >= (int64_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "too many tiles"); return -1; }
-        fg.push_back({s, m, w, np, nrb, (int32_t)ntflag, 0, 0, 0});
+        fg.push_back({s, m, w, np, nrb, (int32_t)ntflag, 0, 0});
         ntflag += (int64_t)np * (nrb + 1);   // one flag per tile of the pivot columns + one per ypre task
       }
       std::stable_sort(fg.begin(), fg.end(), [](const DagFront& a, const DagFront& b) { return a.m > b.m; });
@@ -266,12 +273,27 @@ int Engine::build_plan() {
         f.tbase = (int32_t)tl_cnt.size();
         tl_cnt.resize(tl_cnt.size() + (size_t)f.nrb * f.nrb, 0);
         auto blk_lo = [&](int b) { return b < f.np ? b * NB : f.w + (b - f.np) * NB; };
+        auto blk_of = [&](int row) { return row < f.w ? row / NB : f.np + (row - f.w) / NB; };
+        fl_tmp.clear();
         std::vector<int> ca(f.nrb + 1);
         for (int q = S.child_ptr[f.s]; q < S.child_ptr[f.s + 1]; q++) {
           const int c = S.child_idx[q];
           const int wc = front_w(c), rc = front_m(c) - wc;
           if (rc == 0) continue;
           const int32_t* relc = &S.rel[S.rptr[c] + wc];
+          if (rc <= DAG_SMALL_RC && flat_ok) {
+            // a small child: its entries go to the flat per-tile lists (sorted by destination below)
+            for (int jc = 0; jc < rc; jc++) {
+              const int bj = blk_of(relc[jc]);
+              for (int ic = jc; ic < rc; ic++) {
+                const int bi = blk_of(relc[ic]);
+                fl_tmp.push_back({(int64_t)f.tbase + (int64_t)bj * f.nrb + bi,
+                                  (relc[jc] - blk_lo(bj)) * DAG_LDT + (relc[ic] - blk_lo(bi)), 1 + q - S.child_ptr[f.s], 0,
+                                  (int32_t)(S.cbptr[c] + ic + (int64_t)jc * rc)});
+              }
+            }
+            continue;
+          }
           const int32_t ce = (int32_t)asm_rc.size();
           asm_rc.push_back(rc);
           asm_off.push_back(S.rptr[c] + wc); asm_off.push_back(S.cbptr[c]);
@@ -289,15 +311,46 @@ int Engine::build_plan() {
             }
           }
         }
-        // A entries per 64-column block (amap is sorted by position = row + col * m)
-        f.abase = (int32_t)ta_ptr.size();
+        if (getenv("B2_DAG_DEBUG") && f.m > 600) {
+          int nchild = S.child_ptr[f.s + 1] - S.child_ptr[f.s], small = 0, t00 = tl_cnt[f.tbase], tmax = 0;
+          long long e00 = 0;
+          for (int q = S.child_ptr[f.s]; q < S.child_ptr[f.s + 1]; q++) small += front_m(S.child_idx[q]) - front_w(S.child_idx[q]) <= 32;
+          for (int b = 0; b < f.nrb * f.nrb; b++) tmax = std::max(tmax, (int)tl_cnt[f.tbase + b]);
+          for (size_t t = 0; t < tl_tmp.size(); t++) if (tl_tmp[t].gid == f.tbase) e00 += (long long)(tl_tmp[t].iz - tl_tmp[t].ia) * (tl_tmp[t].jz - tl_tmp[t].ja);
+          fprintf(stderr, "dagfront level %d m %d w %d: children %d (rc <= 32: %d), pairs on tile (0,0) %d (%lld entries), max pairs per tile %d\n", l, f.m, f.w, nchild, small, t00, e00, tmax);
+        }
+        // the A entries of the front (position = row + col * m inside the panel)
         {
           const int32_t* apos = S.amap_pos.data() + S.amap_ptr[f.s];
+          const int32_t* aslot = S.amap_slot.data() + S.amap_ptr[f.s];
           const int64_t na = S.amap_ptr[f.s + 1] - S.amap_ptr[f.s];
-          for (int b = 0; b <= f.nrb; b++) {
-            const int col = b < f.np ? b * NB : f.w;      // blocks of the contribution block hold no A entry
-            ta_ptr.push_back((int32_t)(std::lower_bound(apos, apos + na, (int64_t)col * f.m > INT32_MAX ? INT32_MAX : col * f.m) - apos));
+          if (flat_ok) {
+            for (int64_t q = 0; q < na; q++) {
+              const int j = apos[q] / f.m, i = apos[q] - j * f.m;
+              const int bj = blk_of(j), bi = blk_of(i);
+              fl_tmp.push_back({(int64_t)f.tbase + (int64_t)bj * f.nrb + bi, (j - blk_lo(bj)) * DAG_LDT + (i - blk_lo(bi)), 0, 1, aslot[q]});
+            }
+          } else if (na > 0) { snprintf(g_last_error, sizeof(g_last_error), "contribution-block storage exceeds int32 offsets"); return -1; }
+        }
+        // sort by (tile, destination, A first, children ascending); the first element of a run carries
+        // its length; runs are cut at the staging rounds of the kernel
+        std::sort(fl_tmp.begin(), fl_tmp.end(), [](const FlEnt& a, const FlEnt& b) {
+          return a.gid != b.gid ? a.gid < b.gid : (a.dest != b.dest ? a.dest < b.dest : a.seq < b.seq); });
+        fl_cnt.resize(fl_cnt.size() + (size_t)f.nrb * f.nrb, 0);
+        for (size_t a = 0; a < fl_tmp.size();) {
+          size_t t1 = a;
+          while (t1 < fl_tmp.size() && fl_tmp[t1].gid == fl_tmp[a].gid) t1++;
+          fl_cnt[(size_t)fl_tmp[a].gid] = (int32_t)(t1 - a);
+          for (size_t e = a; e < t1;) {
+            size_t r1 = e + 1;
+            while (r1 < t1 && fl_tmp[r1].dest == fl_tmp[e].dest && ((r1 - a) % DAG_STAGE) != 0) r1++;
+            for (size_t k = e; k < r1; k++) {
+              fl_ent.push_back(fl_tmp[k].dest | (fl_tmp[k].isA << 13) | (k == e ? (int32_t)((r1 - e) << 14) : 0));
+              fl_ent.push_back(fl_tmp[k].src);
+            }
+            e = r1;
           }
+          a = t1;
         }
         dagf.push_back(f);
       }
@@ -305,31 +358,90 @@ int Engine::build_plan() {
       // order): wave 2d holds what can start once pivot block d-1 is factored -- the chain task of
       // block d (first: it is the critical path) and the tiles of column d-1; 2d+1 the ypre task of
       // block d+1; the tiles of the contribution block follow the last column (wave 2 np + 1)
-      struct TK { int key, pri; int32_t s, I, code, fb, df, tbase, abase; };
+      struct TK { int key, pri; int32_t s, I, code, fb, df, tbase; };
       std::vector<TK> tks;
       for (const DagFront& f : fg) {
         const int np = f.np;
         for (int J = 0; J < f.nrb; J++)
           for (int I = J; I < f.nrb; I++) {
-            if (J >= np) { tks.push_back({2 * np + 1, 1, f.s, I, J, f.fb, f.df, f.tbase, f.abase}); continue; }
+            if (J >= np) { tks.push_back({2 * np + 1, 1, f.s, I, J, f.fb, f.df, f.tbase}); continue; }
             if (I == J) {
-              if (J == 0) tks.push_back({0, 0, f.s, 0, 0, f.fb, f.df, f.tbase, f.abase});
+              if (J == 0) tks.push_back({0, 0, f.s, 0, 0, f.fb, f.df, f.tbase});
               continue;                                      // J > 0: part of the chain task of block J
             }
             if (I == J + 1 && I < np) {                      // chain task: tiles (I, I-1) and (I, I) ...
-              tks.push_back({2 * I, 0, f.s, I, I | (1 << 16), f.fb, f.df, f.tbase, f.abase});
+              tks.push_back({2 * I, 0, f.s, I, I | (1 << 16), f.fb, f.df, f.tbase});
               // ... after the task that applies the pivot blocks p < I-1 to (I, I)
-              if (I >= 2) tks.push_back({2 * (I - 1) + 1, 1, f.s, I, I | (2 << 16), f.fb, f.df, f.tbase, f.abase});
+              if (I >= 2) tks.push_back({2 * (I - 1) + 1, 1, f.s, I, I | (2 << 16), f.fb, f.df, f.tbase});
               continue;
             }
-            tks.push_back({2 * (J + 1), 1, f.s, I, J, f.fb, f.df, f.tbase, f.abase});
+            tks.push_back({2 * (J + 1), 1, f.s, I, J, f.fb, f.df, f.tbase});
           }
       }
       std::stable_sort(tks.begin(), tks.end(), [](const TK& a, const TK& b) { return a.key != b.key ? a.key < b.key : a.pri < b.pri; });
-      for (const TK& t : tks) {
-        const int32_t rec[8] = {t.s, t.I, t.code, t.fb, t.tbase, t.abase, 0, t.df};
-        items_dag.insert(items_dag.end(), rec, rec + 8);
-        G.count++;
+      // Ticket order of the whole launch = a simulated schedule.  The tasks are walked in the order
+      // above (topological) with a cost model (us) and unlimited workers: `fin` = earliest finish of
+      // a task given when its inputs appear, key = fin - own work = the latest start that does not
+      // delay it (a left-looking tile started earlier would only hold a CTA while it waits for pivot
+      // blocks).  The key is then raised above the keys of everything the task waits for, so that
+      // sorting by key stays a topological order: a CTA only ever waits for smaller tickets.
+      {
+        constexpr double T_ASM = 8, T_UPD = 2.5, T_LDL = 12.5, T_SUB = 5, T_POST = 2, T_ST = 1, T_EPS = 1e-3;
+        struct FS { double R = 0, KR = 0; std::vector<double> F, KF, Y, KY; };
+        const int df0 = fg.empty() ? 0 : fg[0].df;
+        std::vector<FS> fs(fg.size());
+        f_done.resize(dagf.size(), 0.0); f_kdone.resize(dagf.size(), 0.0);
+        for (size_t i = 0; i < fg.size(); i++) {
+          const DagFront& f = fg[i];
+          fs[i].F.assign((size_t)f.np * f.nrb, 0.0); fs[i].KF.assign((size_t)f.np * f.nrb, 0.0);
+          fs[i].Y.assign(f.np + 1, 0.0); fs[i].KY.assign(f.np + 1, 0.0);
+          for (int q = S.child_ptr[f.s]; q < S.child_ptr[f.s + 1]; q++) {
+            const int dc = dag_of[S.child_idx[q]];
+            if (dc >= 0) { fs[i].R = std::max(fs[i].R, f_done[dc]); fs[i].KR = std::max(fs[i].KR, f_kdone[dc]); }
+          }
+        }
+        for (const TK& t : tks) {
+          const DagFront& f = fg[t.df - df0];
+          FS& X = fs[t.df - df0];
+          const int np = f.np, nrb = f.nrb, kind = t.code >> 16, J = t.code & 0xffff, I = t.I;
+          double tc = X.R + T_ASM, work = T_ASM, kdep = X.KR;
+          auto need = [&](int i, int p) { tc = std::max(tc, X.F[i + (size_t)p * nrb]); kdep = std::max(kdep, X.KF[i + (size_t)p * nrb]); };
+          auto upd = [&]() { tc += T_UPD; work += T_UPD; };
+          double key = 0;
+          if (kind == 0 && J >= np) {                          // tile of the contribution block
+            for (int p2 = 0; p2 < np; p2++) { need(I, p2); need(J, p2); upd(); }
+            tc += T_ST; work += T_ST;
+            key = std::max(tc - work, kdep + T_EPS);
+            f_done[t.df] = std::max(f_done[t.df], tc); f_kdone[t.df] = std::max(f_kdone[t.df], key);
+          } else if (kind == 0 && I == J) {                    // the first diagonal tile
+            tc += T_LDL + T_POST; work += T_LDL + T_POST;
+            key = std::max(tc - work, kdep + T_EPS);
+            X.F[0] = tc; X.KF[0] = key;
+          } else if (kind == 0) {                              // substitution tile (I, J)
+            for (int p2 = 0; p2 < J; p2++) { need(I, p2); need(J, p2); upd(); }
+            need(J, J); tc += T_SUB; work += T_SUB;
+            key = std::max(tc - work, kdep + T_EPS);
+            X.F[I + (size_t)J * nrb] = tc; X.KF[I + (size_t)J * nrb] = key;
+          } else if (kind == 1) {                              // chain task of block J
+            for (int p2 = 0; p2 < J - 1; p2++) { need(J, p2); need(J - 1, p2); upd(); }
+            if (J >= 2) { tc = std::max(tc, X.Y[J]); kdep = std::max(kdep, X.KY[J]); } else { tc += T_ASM; work += T_ASM; }
+            need(J - 1, J - 1); tc += T_SUB; work += T_SUB;
+            const double tsub = tc;
+            tc += T_UPD + T_LDL + T_POST; work += T_UPD + T_LDL + T_POST;
+            key = std::max(tc - work, kdep + T_EPS);
+            X.F[J + (size_t)(J - 1) * nrb] = tsub; X.KF[J + (size_t)(J - 1) * nrb] = key;
+            X.F[J + (size_t)J * nrb] = tc; X.KF[J + (size_t)J * nrb] = key;
+          } else {                                             // ypre task of block J
+            for (int p2 = 0; p2 < J - 1; p2++) { need(J, p2); upd(); }
+            tc += T_ST; work += T_ST;
+            key = std::max(tc - work, kdep + T_EPS);
+            X.Y[J] = tc; X.KY[J] = key;
+          }
+          DTask d; d.key = key;
+          const int32_t rec[8] = {t.s, t.I, t.code, t.fb, t.tbase, 0, 0, t.df};
+          memcpy(d.rec, rec, sizeof(rec));
+          dtasks.push_back(d);
+        }
       }
       continue;
     }
@@ -418,6 +530,12 @@ int Engine::build_plan() {
   }
   // the dataflow launch of the top of the tree: parents' records, absolute counter offsets
   ndag = 0; ndcnt = 0;
+  if (!dtasks.empty()) {
+    if (dag_sched)
+      std::stable_sort(dtasks.begin(), dtasks.end(), [](const DTask& a, const DTask& b) { return a.key < b.key; });
+    for (const DTask& d : dtasks) items_dag.insert(items_dag.end(), d.rec, d.rec + 8);
+    G.count = (int)dtasks.size();
+  }
   if (G.count > 0) {
     const int ndf = (int)dagf.size();
     for (const DagFront& f : dagf) {
@@ -439,15 +557,22 @@ int Engine::build_plan() {
     if (tl_tmp.size() >= (size_t)INT32_MAX / 8) { snprintf(g_last_error, sizeof(g_last_error), "too many extend-add pairs"); return -1; }
     std::vector<int32_t> tl_ptr(tl_cnt.size() + 1, 0);
     for (size_t i = 0; i < tl_cnt.size(); i++) tl_ptr[i + 1] = tl_ptr[i] + tl_cnt[i];
-    std::vector<int32_t> fill(tl_ptr.begin(), tl_ptr.end() - 1), tl_ent(6 * tl_tmp.size(), 0);
+    std::vector<int32_t> fill(tl_ptr.begin(), tl_ptr.end() - 1), tl_ent(8 * tl_tmp.size(), 0);
     for (const TlEnt& e : tl_tmp) {
-      int32_t* d = &tl_ent[6 * (size_t)fill[e.gid]++];
-      d[0] = e.ce; d[1] = e.ia; d[2] = e.iz; d[3] = e.ja; d[4] = e.jz;
+      int32_t* d = &tl_ent[8 * (size_t)fill[e.gid]++];
+      const int64_t cbo = asm_off[2 * (size_t)e.ce + 1];
+      d[0] = e.ia; d[1] = e.iz; d[2] = e.ja; d[3] = e.jz; d[4] = asm_rc[e.ce];
+      d[5] = (int32_t)asm_off[2 * (size_t)e.ce];          // < 2^31: checked below (front row storage)
+      d[6] = (int32_t)(uint32_t)(cbo & 0xffffffffll); d[7] = (int32_t)(cbo >> 32);
     }
     if (upload(&d_tl_ptr, tl_ptr, bytes_device)) return -1;
     if (upload(&d_tl_ent, tl_ent, bytes_device)) return -1;
-    if (upload(&d_ta_ptr, ta_ptr, bytes_device)) return -1;
-    plan.dfr = d_dfr; plan.tl_ptr = d_tl_ptr; plan.tl_ent = d_tl_ent; plan.ta_ptr = d_ta_ptr;
+    if (fl_ent.size() / 2 >= (size_t)INT32_MAX) { snprintf(g_last_error, sizeof(g_last_error), "too many flat extend-add elements"); return -1; }
+    std::vector<int32_t> fl_ptr(fl_cnt.size() + 1, 0);
+    for (size_t i = 0; i < fl_cnt.size(); i++) fl_ptr[i + 1] = fl_ptr[i] + fl_cnt[i];
+    if (upload(&d_fl_ptr, fl_ptr, bytes_device)) return -1;
+    if (upload(&d_fl_ent, fl_ent, bytes_device)) return -1;
+    plan.dfr = d_dfr; plan.tl_ptr = d_tl_ptr; plan.tl_ent = d_tl_ent; plan.fl_ptr = d_fl_ptr; plan.fl_ent = d_fl_ent;
   }
   // staging area of the factored diagonal blocks + the write-back launch that ends a factorization
   {
@@ -622,7 +747,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_ta_ptr, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_fl_ptr, d_fl_ent, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_mismatch) cudaFreeHost(h_mismatch);
   if (cstream) cudaStreamDestroy(cstream);

@@ -60,8 +60,9 @@ struct Engine {
   bool use_dag = true;
   int dag_level_max = 600;     // ... covering the highest run of tree levels with at most this many fronts each (B2_DAG_LEVEL_MAX)
   int dag_from_level = 0;      // first level of the dataflow launch (== nlevels: none)
+  bool dag_sched = true;       // ticket order = simulated schedule (B2_DAG_SCHED=0: level by level, wave by wave)
   int64_t ndcnt = 0;           // counters of the dataflow launch (after the tile flags and the ticket)
-  int32_t *d_dfr = nullptr, *d_tl_ptr = nullptr, *d_tl_ent = nullptr, *d_ta_ptr = nullptr;
+  int32_t *d_dfr = nullptr, *d_tl_ptr = nullptr, *d_tl_ent = nullptr, *d_fl_ptr = nullptr, *d_fl_ent = nullptr;
   int dag_excl_max = 0;        // k_front_dag launches with at most this many tasks run one CTA per SM (B2_DAG_EXCL_MAX)
   int dag_ctas = 0;            // CTAs of a k_front_dag launch (resident CTAs of the device)
   int64_t ntflag = 0;          // tile flags of all tiled fronts; the ticket counters of the launches follow them

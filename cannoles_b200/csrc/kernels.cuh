@@ -364,6 +364,9 @@ __device__ __forceinline__ double rcp_cubic(double d) {
 // back into S and the reciprocal pivots into rds
 // (not inlined: one copy per kernel instead of one per call site -- the fully unrolled body is ~9 KB
 // of SASS and the code around the pivot chain runs cold, instruction fetch included)
+// (measured and rejected in round 2: spreading the 8 x 8 block over the lanes -- two entries per lane,
+// nine 64-bit shuffles per 2 x 2 pivot step -- takes 2440 cycles per panel against 1816 for this
+// redundant form: scripts/_dev/ldlt_microbench.cu, 28.3 k vs 24.3 k cycles per 64 x 64 tile)
 __device__ __noinline__ void warp_ldlt8(double* S, int kb, int pw, double* rds, int* flags) {
   constexpr int ld = DIAG_LD;
   double g[8][8], rd[8];
@@ -930,45 +933,57 @@ __device__ __forceinline__ double frag_c2a(double c0, double c1, int h, int lane
   return (lane & 1) ? v1 : v0;
 }
 
-// Extend-add of ONE NB x NB tile of a front in shared memory: Ts[col * DAG_LDT + row].  The host lists,
-// per tile, the children whose contribution block lands on it with the ranges of child rows / child
-// columns that fall into the tile's row / column block (tl_ptr / tl_ent: child descriptor, ia, iz, ja,
-// jz), children ascending; per 64-column block of the front the range of its A entries (ta_ptr).
-constexpr int DAG_DESC = 32;                     // child descriptors staged per round
-__device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int s, int m, int i0, int iend, int j0,
-                                                  int tgid, int agid, double* Ts, long long* sdesc) {
+// Extend-add of ONE NB x NB tile of a front in shared memory: Ts[col * DAG_LDT + row].
+// A separator front has one tiny child per pivot column (the r / lambda leaves hanging off its
+// variables: ~80 children land on a diagonal tile, one or two entries each) and two big ones.
+//  * the A entries and everything that comes from small children (order of the contribution block
+//    <= DAG_SMALL_RC) are a FLAT list per tile, built and sorted by destination on the host
+//    (fl_ptr / fl_ent: destination | A flag | run length, source offset): one parallel gather into a
+//    staging area, then the first element of every run sums its run in list order (A entry first,
+//    children ascending) -- two barriers whatever the number of children (a barrier and a round of
+//    dependent loads per child made the diagonal tile of every front a 50 us task);
+//  * big children are listed per tile (tl_ptr / tl_ent, self-contained entries: child rows [ia, iz)
+//    / child columns [ja, jz) of the tile's row / column block, order of the child's block, offsets
+//    of its rel[] and of the block) and added one after the other, a warp per child column.
+// Fixed order, no atomics: deterministic sums.
+constexpr int DAG_DESC = 32;                     // child descriptors staged per round (8 ints each)
+constexpr int DAG_STAGE = 4096;                  // elements of the flat list gathered per round
+constexpr int DAG_SMALL_RC = 32;
+__device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int i0, int j0, int tgid, double* Ts,
+                                                  double* stage, int* sdesc) {
   constexpr int LDT = DAG_LDT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int idx = tid; idx < NB * LDT; idx += 256) Ts[idx] = 0.0;
   const int e0 = P.tl_ptr[tgid], e1 = P.tl_ptr[tgid + 1];
-  __syncthreads();
-  {
-    const int64_t a0 = P.amap_ptr[s];
-    const int64_t qa = a0 + P.ta_ptr[agid], qb = a0 + P.ta_ptr[agid + 1];
-    for (int64_t q = qa + tid; q < qb; q += 256) {
-      const int pos = P.amap_pos[q];
-      const int j = pos / m, i = pos - j * m;
-      if (i >= i0 && i < iend) Ts[(j - j0) * LDT + (i - i0)] = P.nzval[P.amap_slot[q]];
+  const int f0 = P.fl_ptr[tgid], f1 = P.fl_ptr[tgid + 1];
+  for (int idx = tid; idx < NB * LDT; idx += 256) Ts[idx] = 0.0;
+  int cnt = min(DAG_DESC, e1 - e0);
+  if (tid < 8 * cnt) sdesc[tid] = P.tl_ent[8 * (size_t)e0 + tid];
+  for (int fb = f0; fb < f1; fb += DAG_STAGE) {
+    const int n = min(DAG_STAGE, f1 - fb);
+    const int32_t* fe = P.fl_ent + 2 * (size_t)fb;
+    for (int e = tid; e < n; e += 256) {
+      const int w0 = fe[2 * e], w1 = fe[2 * e + 1];
+      stage[e] = (w0 & (1 << 13)) ? P.nzval[w1] : P.CB[w1];
     }
-  }
-  for (int eb = e0; eb < e1; eb += DAG_DESC) {
-    const int cnt = min(DAG_DESC, e1 - eb);
-    __syncthreads();                             // A entries placed / previous round consumed
-    if (tid < cnt) {
-      // descriptor of child eb + tid: offsets of its rel[] and of its contribution block, its order
-      const int32_t* d = P.tl_ent + 6 * (size_t)(eb + tid);
-      const int ce = d[0];
-      sdesc[4 * tid] = P.asm_off[2 * ce];
-      sdesc[4 * tid + 1] = P.asm_off[2 * ce + 1];
-      sdesc[4 * tid + 2] = ((long long)d[1] << 32) | (unsigned)d[2];
-      sdesc[4 * tid + 3] = ((long long)P.asm_rc[ce] << 48) | ((long long)d[3] << 24) | (long long)d[4];
+    __syncthreads();                             // (also: the tile is zeroed / the previous round is summed)
+    for (int e = tid; e < n; e += 256) {
+      const int w0 = fe[2 * e];
+      const int rl = w0 >> 14;
+      if (rl) {
+        double sum = Ts[w0 & 0x1fff];
+        for (int k = 0; k < rl; k++) sum += stage[e + k];
+        Ts[w0 & 0x1fff] = sum;
+      }
     }
     __syncthreads();
+  }
+  if (f0 >= f1) __syncthreads();                 // the tile is zeroed, the descriptors are in place
+  for (int eb = e0; eb < e1;) {
     for (int k = 0; k < cnt; k++) {
-      const int32_t* relc = P.rel + sdesc[4 * k];
-      const double* cb = P.CB + sdesc[4 * k + 1];
-      const int ia = (int)(sdesc[4 * k + 2] >> 32), iz = (int)(sdesc[4 * k + 2] & 0xffffffffll);
-      const int rc = (int)(sdesc[4 * k + 3] >> 48), ja = (int)((sdesc[4 * k + 3] >> 24) & 0xffffff), jz = (int)(sdesc[4 * k + 3] & 0xffffff);
+      const int* d = sdesc + 8 * k;
+      const int ia = d[0], iz = d[1], ja = d[2], jz = d[3], rc = d[4];
+      const int32_t* relc = P.rel + d[5];
+      const double* cb = P.CB + (((long long)d[7] << 32) | (unsigned)d[6]);
       // warp <-> child column, lanes over the child rows of the tile's row block (contiguous in the
       // child's contribution block); within one child every entry has its own destination
       for (int j = ja + warp; j < jz; j += 8) {
@@ -978,8 +993,12 @@ __device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int s, int m
       }
       __syncthreads();                           // the next child may land on the same entries
     }
+    eb += DAG_DESC;
+    if (eb >= e1) break;
+    cnt = min(DAG_DESC, e1 - eb);
+    if (tid < 8 * cnt) sdesc[tid] = P.tl_ent[8 * (size_t)eb + tid];
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* __restrict__ items, int ntasks,
@@ -993,7 +1012,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
   double* Mi = Lr + NB * LDL;                    // inverses of the 8 x 8 diagonal blocks of L(J,J), row-major
   double* rdv = Mi + 8 * 64;                     // 1 / d of the pivot block
   __shared__ int s_tk;
-  __shared__ long long sdesc[4 * DAG_DESC];
+  __shared__ int sdesc[8 * DAG_DESC];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp & 1, wc = warp >> 1;       // warp tile of the update: rows wr*32.., cols wc*16..
@@ -1038,6 +1057,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
       if (tid == 0) dag_wait_count(P.dcnt + P.dcnt_ch + df, fr[3]);
       __syncthreads();
     }
+    DAG_TRACE(10);
     // ---- the update(s): one tile, or (J, J-1) then (J, J) of a chain task ------------------
     for (int ph = 0; ph < (chain ? 2 : 1); ph++) {
       const int Jt = (chain && ph == 0) ? J - 1 : J;            // column block of this tile
@@ -1072,7 +1092,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
               cold[a][cc][e] = ok ? dag_ld(Lp + ri + (size_t)cj * m) : 0.0;
             }
       } else {
-        dag_assemble_tile(P, s, m, i0, iend, j0, it[4] + Jt * nrb + I, it[5] + Jt, As, sdesc);
+        dag_assemble_tile(P, i0, j0, it[4] + Jt * nrb + I, As, Lr, sdesc);
         B2_UNROLL
         for (int a = 0; a < 4; a++)
           B2_UNROLL
@@ -1084,6 +1104,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
               cold[a][cc][e] = ok ? As[lj * LDT + li] : 0.0;
             }
         __syncthreads();                         // As | Bs go back to the operand pipeline
+        if (ph == 0) DAG_TRACE(11);
       }
       const int nchunk = (Ktot + KC - 1) / KC;
       if (nchunk > 0) {

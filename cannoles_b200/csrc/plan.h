@@ -41,8 +41,9 @@ struct PlanDev {
   int* dcnt;
   int dcnt_cb, dcnt_ch;
   const int32_t* tl_ptr;   // per tile of the dataflow fronts (first list + J * nrb + I): range in tl_ent
-  const int32_t* tl_ent;   // 6 ints: child descriptor (asm_rc / asm_off), child rows [ia, iz), child columns [ja, jz), -
-  const int32_t* ta_ptr;   // per 64-column block of the dataflow fronts: range of its A entries relative to amap_ptr[front]
+  const int32_t* tl_ent;   // 8 ints: child rows [ia, iz), child columns [ja, jz), order of its contribution block, offset of its rel[], offset of the block (lo, hi)
+  const int32_t* fl_ptr;   // per tile: range in fl_ent of the flat extend-add list (A entries + small children)
+  const int32_t* fl_ent;   // 2 ints: destination in the tile (13 bits) | A flag (bit 13) | run length << 14 (first of a run), source offset (nzval slot / CB)
 };
 
 constexpr int NB = 64;        // pivot block width of the tiled path (== TILE: tile (0,0) is the next diagonal block)
