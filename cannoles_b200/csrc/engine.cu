@@ -72,7 +72,7 @@ int Engine::build_plan() {
     if (any_large) dag_from_level = l;
   }
   struct DagFront { int s, m, w, np, nrb; int32_t fb, df, tbase; };
-  struct TlEnt { int64_t gid; int32_t ce, ia, iz, ja, jz; };
+  struct TlEnt { int64_t gid; int32_t ce, ia, iz, ja, jz, rlo, clo; };
   struct FlEnt { int64_t gid; int32_t dest, seq, isA, src; };
   struct DTask { double key; int32_t rec[8]; };
   std::vector<DTask> dtasks;                        // tasks of the dataflow launch with their schedule keys
@@ -306,7 +306,7 @@ int Engine::build_plan() {
             if (ca[bj] == ca[bj + 1]) continue;
             for (int bi = bj; bi < f.nrb; bi++) {
               if (ca[bi] == ca[bi + 1]) continue;
-              tl_tmp.push_back({(int64_t)f.tbase + (int64_t)bj * f.nrb + bi, ce, ca[bi], ca[bi + 1], ca[bj], ca[bj + 1]});
+              tl_tmp.push_back({(int64_t)f.tbase + (int64_t)bj * f.nrb + bi, ce, ca[bi], ca[bi + 1], ca[bj], ca[bj + 1], blk_lo(bi), blk_lo(bj)});
               tl_cnt[(size_t)f.tbase + (size_t)bj * f.nrb + bi]++;
             }
           }
@@ -551,19 +551,75 @@ int Engine::build_plan() {
     fact_launches.push_back(G);
     ndag = 1;
   }
+  // flat extend-add lists of the fronts that stay in shared memory (k_front_small)
+  plan.sf_ptr = nullptr; plan.sf_ent = nullptr;
+  if (flat_ok && small_max_m <= 181) {
+    std::vector<int64_t> sf_ptr(S.nsuper + 1, 0);
+    for (int s = 0; s < S.nsuper; s++) {
+      int64_t n = 0;
+      const int m = front_m(s);
+      if (m <= (int)small_max_m && m > tiny_max_m && !front_dag[s]) {
+        n = S.amap_ptr[s + 1] - S.amap_ptr[s];
+        for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
+          const int64_t rc = front_m(S.child_idx[q]) - front_w(S.child_idx[q]);
+          n += rc * (rc + 1) / 2;
+        }
+      }
+      sf_ptr[s + 1] = sf_ptr[s] + n;
+    }
+    if (sf_ptr[S.nsuper] > 0 && sf_ptr[S.nsuper] <= flat_small_max) {
+      std::vector<int32_t> sf_ent(2 * (size_t)sf_ptr[S.nsuper]);
+      struct El { int32_t dest, seq, isA, src; };
+      std::vector<El> el;
+      for (int s = 0; s < S.nsuper; s++) {
+        if (sf_ptr[s + 1] == sf_ptr[s]) continue;
+        const int m = front_m(s);
+        el.clear();
+        for (int64_t q = S.amap_ptr[s]; q < S.amap_ptr[s + 1]; q++) el.push_back({S.amap_pos[q], 0, 1, S.amap_slot[q]});
+        for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; q++) {
+          const int c = S.child_idx[q];
+          const int wc = front_w(c), rc = front_m(c) - wc;
+          const int32_t* relc = &S.rel[S.rptr[c] + wc];
+          for (int j = 0; j < rc; j++)
+            for (int i = j; i < rc; i++)
+              el.push_back({relc[i] + relc[j] * m, 1 + q - S.child_ptr[s], 0, (int32_t)(S.cbptr[c] + i + (int64_t)j * rc)});
+        }
+        std::sort(el.begin(), el.end(), [](const El& a, const El& b) { return a.dest != b.dest ? a.dest < b.dest : a.seq < b.seq; });
+        int32_t* out = &sf_ent[2 * (size_t)sf_ptr[s]];
+        for (size_t e = 0; e < el.size();) {
+          size_t r1 = e + 1;
+          while (r1 < el.size() && el[r1].dest == el[e].dest && r1 - e < 65535) r1++;
+          for (size_t k = e; k < r1; k++) {
+            out[2 * k] = el[k].dest | (el[k].isA << 15) | (k == e ? (int32_t)((uint32_t)(r1 - e) << 16) : 0);
+            out[2 * k + 1] = el[k].src;
+          }
+          e = r1;
+        }
+      }
+      if (upload(&d_sf_ptr, sf_ptr, bytes_device)) return -1;
+      if (upload(&d_sf_ent, sf_ent, bytes_device)) return -1;
+      plan.sf_ptr = d_sf_ptr; plan.sf_ent = d_sf_ent;
+    }
+  }
   if (upload(&d_dfr, dfr, bytes_device)) return -1;
   {
     // per-tile child lists: counting sort of the (tile, child) pairs by tile (children stay ascending)
     if (tl_tmp.size() >= (size_t)INT32_MAX / 8) { snprintf(g_last_error, sizeof(g_last_error), "too many extend-add pairs"); return -1; }
     std::vector<int32_t> tl_ptr(tl_cnt.size() + 1, 0);
     for (size_t i = 0; i < tl_cnt.size(); i++) tl_ptr[i + 1] = tl_ptr[i] + tl_cnt[i];
-    std::vector<int32_t> fill(tl_ptr.begin(), tl_ptr.end() - 1), tl_ent(8 * tl_tmp.size(), 0);
+    std::vector<int32_t> fill(tl_ptr.begin(), tl_ptr.end() - 1), tl_ent((size_t)DAG_ENT * tl_tmp.size(), 0);
     for (const TlEnt& e : tl_tmp) {
-      int32_t* d = &tl_ent[8 * (size_t)fill[e.gid]++];
+      int32_t* d = &tl_ent[(size_t)DAG_ENT * fill[e.gid]++];
       const int64_t cbo = asm_off[2 * (size_t)e.ce + 1];
-      d[0] = e.ia; d[1] = e.iz; d[2] = e.ja; d[3] = e.jz; d[4] = asm_rc[e.ce];
-      d[5] = (int32_t)asm_off[2 * (size_t)e.ce];          // < 2^31: checked below (front row storage)
-      d[6] = (int32_t)(uint32_t)(cbo & 0xffffffffll); d[7] = (int32_t)(cbo >> 32);
+      d[0] = asm_rc[e.ce];
+      d[1] = (int32_t)(uint32_t)(cbo & 0xffffffffll); d[2] = (int32_t)(cbo >> 32);
+      // the child rows [ia, iz) land on rows rel - rlo of the tile, its columns [ja, jz) on columns rel - clo
+      uint16_t* rmap = reinterpret_cast<uint16_t*>(d + 8);
+      uint16_t* cmap = rmap + 64;
+      for (int k = 0; k < 128; k++) rmap[k] = 0xffff;
+      const int32_t* relc = &S.rel[asm_off[2 * (size_t)e.ce]];
+      for (int i = e.ia; i < e.iz; i++) rmap[relc[i] - e.rlo] = (uint16_t)i;
+      for (int j = e.ja; j < e.jz; j++) cmap[relc[j] - e.clo] = (uint16_t)j;
     }
     if (upload(&d_tl_ptr, tl_ptr, bytes_device)) return -1;
     if (upload(&d_tl_ent, tl_ent, bytes_device)) return -1;
@@ -747,7 +803,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_fl_ptr, d_fl_ent, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_fl_ptr, d_fl_ent, d_sf_ptr, d_sf_ent, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_mismatch) cudaFreeHost(h_mismatch);
   if (cstream) cudaStreamDestroy(cstream);

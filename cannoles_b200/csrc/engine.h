@@ -62,6 +62,9 @@ struct Engine {
   int dag_from_level = 0;      // first level of the dataflow launch (== nlevels: none)
   bool dag_sched = true;       // ticket order = simulated schedule (B2_DAG_SCHED=0: level by level, wave by wave)
   int64_t ndcnt = 0;           // counters of the dataflow launch (after the tile flags and the ticket)
+  int64_t* d_sf_ptr = nullptr;
+  int32_t* d_sf_ent = nullptr;
+  int64_t flat_small_max = (int64_t)1 << 29;   // flat extend-add lists of the small fronts: at most this many elements (8 bytes each)
   int32_t *d_dfr = nullptr, *d_tl_ptr = nullptr, *d_tl_ent = nullptr, *d_fl_ptr = nullptr, *d_fl_ent = nullptr;
   int dag_excl_max = 0;        // k_front_dag launches with at most this many tasks run one CTA per SM (B2_DAG_EXCL_MAX)
   int dag_ctas = 0;            // CTAs of a k_front_dag launch (resident CTAs of the device)

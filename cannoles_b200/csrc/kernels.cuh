@@ -107,6 +107,26 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
 
   for (int idx = tid; idx < m * m; idx += NT) F[idx] = 0.0;
   B2_FSYNC();
+  if (P.sf_ptr != nullptr) {
+    // extend-add from a flat list built and sorted by destination on the host (A entry first, then
+    // the children ascending: the sums of the loop below, bit for bit): the first element of a run
+    // sums its run.  Two dependent loads for the whole front instead of a barrier and a chain of
+    // five dependent loads per child -- a front of the bottom levels has a dozen one-entry children.
+    const int64_t e1 = P.sf_ptr[s + 1];
+    for (int64_t e = P.sf_ptr[s] + tid; e < e1; e += NT) {
+      const int w0 = P.sf_ent[2 * e];
+      const int rl = (int)((unsigned)w0 >> 16);
+      if (rl) {
+        double sum = 0.0;
+        for (int k = 0; k < rl; k++) {
+          const int wk = P.sf_ent[2 * (e + k)], src = P.sf_ent[2 * (e + k) + 1];
+          sum += (wk & (1 << 15)) ? P.nzval[src] : P.CB[src];
+        }
+        F[w0 & 0x7fff] = sum;
+      }
+    }
+    B2_FSYNC();
+  } else {
   for (int64_t q = P.amap_ptr[s] + tid; q < P.amap_ptr[s + 1]; q += NT)
     F[P.amap_pos[q]] = P.nzval[P.amap_slot[q]];
   B2_FSYNC();
@@ -122,6 +142,7 @@ __global__ void __launch_bounds__(NT * FPB) k_front_small(PlanDev P, const int32
       for (int i = j + lane; i < rc; i += 32) F[relc[i] + J * m] += cb[i + (size_t)j * rc];
     }
     B2_FSYNC();
+  }
   }
   // eliminate the w pivot columns: rank-1 updates restricted to the pivot columns ...
   for (int k = 0; k < w; k++) {
@@ -933,31 +954,73 @@ __device__ __forceinline__ double frag_c2a(double c0, double c1, int h, int lane
   return (lane & 1) ? v1 : v0;
 }
 
-// Extend-add of ONE NB x NB tile of a front in shared memory: Ts[col * DAG_LDT + row].
+// Extend-add of ONE NB x NB tile of a front, straight into the registers that hold the tile as C
+// fragments (cold[a][cc][e] <-> row wr*32 + a*8 + g, column wc*16 + cc*8 + 2t + e).
 // A separator front has one tiny child per pivot column (the r / lambda leaves hanging off its
 // variables: ~80 children land on a diagonal tile, one or two entries each) and two big ones.
+//  * big children are listed per tile (tl_ptr / tl_ent, children ascending).  An entry is
+//    self-contained -- order of the child's contribution block, its offset, and for the 64 rows and
+//    the 64 columns of the tile the child row / column that lands there (uint16, 0xffff: none) -- so
+//    every thread gathers ITS 16 entries by destination: no shared-memory tile, no barrier between
+//    children, all loads of all children independent of each other;
 //  * the A entries and everything that comes from small children (order of the contribution block
 //    <= DAG_SMALL_RC) are a FLAT list per tile, built and sorted by destination on the host
 //    (fl_ptr / fl_ent: destination | A flag | run length, source offset): one parallel gather into a
 //    staging area, then the first element of every run sums its run in list order (A entry first,
-//    children ascending) -- two barriers whatever the number of children (a barrier and a round of
-//    dependent loads per child made the diagonal tile of every front a 50 us task);
-//  * big children are listed per tile (tl_ptr / tl_ent, self-contained entries: child rows [ia, iz)
-//    / child columns [ja, jz) of the tile's row / column block, order of the child's block, offsets
-//    of its rel[] and of the block) and added one after the other, a warp per child column.
-// Fixed order, no atomics: deterministic sums.
-constexpr int DAG_DESC = 32;                     // child descriptors staged per round (8 ints each)
+//    children ascending) into a shared-memory tile -- two barriers whatever the number of children;
+//    a tile without such entries (most tiles away from the diagonal) skips this part.
+// Sum per entry: big children ascending, then + (A + small children ascending).  Fixed order, no
+// atomics: deterministic.
+constexpr int DAG_ENT = 72;                      // ints per tl_ent entry: 8 header + 64 (128 uint16 maps)
+constexpr int DAG_DESC = 3;                      // entries staged per round
 constexpr int DAG_STAGE = 4096;                  // elements of the flat list gathered per round
 constexpr int DAG_SMALL_RC = 32;
-__device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int i0, int j0, int tgid, double* Ts,
-                                                  double* stage, int* sdesc) {
+__device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int tgid, double* Ts, double* stage, int* sdesc,
+                                                  double (&cold)[4][2][2]) {
   constexpr int LDT = DAG_LDT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3, wr = warp & 1, wc = warp >> 1;
   const int e0 = P.tl_ptr[tgid], e1 = P.tl_ptr[tgid + 1];
   const int f0 = P.fl_ptr[tgid], f1 = P.fl_ptr[tgid + 1];
-  for (int idx = tid; idx < NB * LDT; idx += 256) Ts[idx] = 0.0;
-  int cnt = min(DAG_DESC, e1 - e0);
-  if (tid < 8 * cnt) sdesc[tid] = P.tl_ent[8 * (size_t)e0 + tid];
+  B2_UNROLL
+  for (int a = 0; a < 4; a++)
+    B2_UNROLL
+    for (int cc = 0; cc < 2; cc++) { cold[a][cc][0] = 0.0; cold[a][cc][1] = 0.0; }
+  if (f1 > f0)
+    for (int idx = tid; idx < NB * LDT; idx += 256) Ts[idx] = 0.0;
+  for (int eb = e0; eb < e1; eb += DAG_DESC) {
+    const int cnt = min(DAG_DESC, e1 - eb);
+    if (tid < DAG_ENT * cnt) sdesc[tid] = P.tl_ent[DAG_ENT * (size_t)eb + tid];      // DAG_ENT * DAG_DESC <= 256
+    __syncthreads();
+    for (int k = 0; k < cnt; k++) {
+      const int* d = sdesc + DAG_ENT * k;
+      const int rc = d[0];
+      const double* cb = P.CB + (((long long)d[2] << 32) | (unsigned)d[1]);
+      const unsigned short* rmap = reinterpret_cast<const unsigned short*>(d + 8);
+      const unsigned short* cmap = rmap + 64;
+      int ri[4], cj[2][2];
+      B2_UNROLL
+      for (int a = 0; a < 4; a++) ri[a] = rmap[wr * 32 + a * 8 + g];
+      B2_UNROLL
+      for (int cc = 0; cc < 2; cc++) { cj[cc][0] = cmap[wc * 16 + cc * 8 + 2 * t]; cj[cc][1] = cmap[wc * 16 + cc * 8 + 2 * t + 1]; }
+      double v[4][2][2];
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int cc = 0; cc < 2; cc++)
+          B2_UNROLL
+          for (int e = 0; e < 2; e++) {
+            const bool ok = ri[a] != 0xffff && cj[cc][e] != 0xffff && ri[a] >= cj[cc][e];
+            v[a][cc][e] = ok ? cb[ri[a] + (size_t)cj[cc][e] * rc] : 0.0;
+          }
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int cc = 0; cc < 2; cc++) { cold[a][cc][0] += v[a][cc][0]; cold[a][cc][1] += v[a][cc][1]; }
+    }
+    if (eb + DAG_DESC < e1) __syncthreads();     // the descriptors are overwritten by the next round
+  }
+  if (f1 <= f0) return;
   for (int fb = f0; fb < f1; fb += DAG_STAGE) {
     const int n = min(DAG_STAGE, f1 - fb);
     const int32_t* fe = P.fl_ent + 2 * (size_t)fb;
@@ -977,28 +1040,13 @@ __device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int i0, int 
     }
     __syncthreads();
   }
-  if (f0 >= f1) __syncthreads();                 // the tile is zeroed, the descriptors are in place
-  for (int eb = e0; eb < e1;) {
-    for (int k = 0; k < cnt; k++) {
-      const int* d = sdesc + 8 * k;
-      const int ia = d[0], iz = d[1], ja = d[2], jz = d[3], rc = d[4];
-      const int32_t* relc = P.rel + d[5];
-      const double* cb = P.CB + (((long long)d[7] << 32) | (unsigned)d[6]);
-      // warp <-> child column, lanes over the child rows of the tile's row block (contiguous in the
-      // child's contribution block); within one child every entry has its own destination
-      for (int j = ja + warp; j < jz; j += 8) {
-        double* dst = Ts + (relc[j] - j0) * LDT - i0;
-        const double* src = cb + (size_t)j * rc;
-        for (int i = max(ia, j) + lane; i < iz; i += 32) dst[relc[i]] += src[i];
-      }
-      __syncthreads();                           // the next child may land on the same entries
-    }
-    eb += DAG_DESC;
-    if (eb >= e1) break;
-    cnt = min(DAG_DESC, e1 - eb);
-    if (tid < 8 * cnt) sdesc[tid] = P.tl_ent[8 * (size_t)eb + tid];
-    __syncthreads();
-  }
+  B2_UNROLL
+  for (int a = 0; a < 4; a++)
+    B2_UNROLL
+    for (int cc = 0; cc < 2; cc++)
+      B2_UNROLL
+      for (int e = 0; e < 2; e++) cold[a][cc][e] += Ts[(wc * 16 + cc * 8 + 2 * t + e) * LDT + wr * 32 + a * 8 + g];
+  __syncthreads();                               // Ts (= As | Bs) goes back to the operand pipeline
 }
 
 __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* __restrict__ items, int ntasks,
@@ -1012,7 +1060,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
   double* Mi = Lr + NB * LDL;                    // inverses of the 8 x 8 diagonal blocks of L(J,J), row-major
   double* rdv = Mi + 8 * 64;                     // 1 / d of the pivot block
   __shared__ int s_tk;
-  __shared__ int sdesc[8 * DAG_DESC];
+  __shared__ int sdesc[DAG_ENT * DAG_DESC];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp & 1, wc = warp >> 1;       // warp tile of the update: rows wr*32.., cols wc*16..
@@ -1092,18 +1140,7 @@ __global__ void __launch_bounds__(256, 2) k_front_dag(PlanDev P, const int32_t* 
               cold[a][cc][e] = ok ? dag_ld(Lp + ri + (size_t)cj * m) : 0.0;
             }
       } else {
-        dag_assemble_tile(P, i0, j0, it[4] + Jt * nrb + I, As, Lr, sdesc);
-        B2_UNROLL
-        for (int a = 0; a < 4; a++)
-          B2_UNROLL
-          for (int cc = 0; cc < 2; cc++)
-            B2_UNROLL
-            for (int e = 0; e < 2; e++) {
-              const int li = wr * 32 + a * 8 + g, lj = wc * 16 + cc * 8 + 2 * t + e;
-              const bool ok = i0 + li < iend && j0 + lj < jend && i0 + li >= j0 + lj;
-              cold[a][cc][e] = ok ? As[lj * LDT + li] : 0.0;
-            }
-        __syncthreads();                         // As | Bs go back to the operand pipeline
+        dag_assemble_tile(P, it[4] + Jt * nrb + I, As, Lr, sdesc, cold);
         if (ph == 0) DAG_TRACE(11);
       }
       const int nchunk = (Ktot + KC - 1) / KC;

@@ -41,7 +41,9 @@ struct PlanDev {
   int* dcnt;
   int dcnt_cb, dcnt_ch;
   const int32_t* tl_ptr;   // per tile of the dataflow fronts (first list + J * nrb + I): range in tl_ent
-  const int32_t* tl_ent;   // 8 ints: child rows [ia, iz), child columns [ja, jz), order of its contribution block, offset of its rel[], offset of the block (lo, hi)
+  const int32_t* tl_ent;   // 72 ints: order of the child's contribution block, offset of the block (lo, hi), 5 x -, then 64 + 64 uint16: child row / column landing on each row / column of the tile (0xffff: none)
+  const int64_t* sf_ptr;   // fronts of the shared-memory path: range in sf_ent of the flat extend-add list (nullptr: per-child loop)
+  const int32_t* sf_ent;   // 2 ints: position in the front (15 bits) | A flag (bit 15) | run length << 16 (first of a run), source offset
   const int32_t* fl_ptr;   // per tile: range in fl_ent of the flat extend-add list (A entries + small children)
   const int32_t* fl_ent;   // 2 ints: destination in the tile (13 bits) | A flag (bit 13) | run length << 14 (first of a run), source offset (nzval slot / CB)
 };
