@@ -38,6 +38,55 @@ bool order_metis_nd(int64_t n, const std::vector<int64_t>& xadj, const std::vect
 }
 
 
+// Nested dissection of the COMPRESSED graph of a KKT matrix [H J'; J -D] (D diagonal): the r / lambda
+// vertices (index >= nvar) only touch x vertices, their pivots are -1 / -delta whatever the order
+// (SURVEY App. B), and eliminating one of them first makes a clique of its x-neighbours -- which is
+// exactly an edge set of the graph G' of H + J'J on the nvar x-vertices.  So: dissect G' (a third
+// of the vertices of the raw graph for config 4, and separators counted in x-vertices only: the
+// critical path of the factorization is the sum of the separator sizes), then order all r / lambda
+// vertices first and the x-vertices in the dissection order; the postorder of the elimination tree
+// hangs every r / lambda leaf under the first of its x-neighbours.
+// Returns false (perm untouched) when the trailing block is not diagonal: the caller dissects the
+// raw graph instead.
+bool order_kkt_compressed_nd(int64_t n, int64_t nvar, const std::vector<int64_t>& xadj,
+                             const std::vector<int64_t>& adj, std::vector<int32_t>& perm, std::string& err) {
+  if (nvar <= 0 || nvar >= n) return false;
+  for (int64_t v = nvar; v < n; v++)
+    for (int64_t p = xadj[v]; p < xadj[v + 1]; p++)
+      if (adj[p] >= nvar) return false;
+  // adjacency of G' with a marker array: sum over rows of |N(v)|^2 steps, no sort
+  std::vector<int64_t> gx(nvar + 1, 0), ga;
+  std::vector<int64_t> mark(nvar, -1);
+  {
+    double work = 0;
+    for (int64_t v = nvar; v < n; v++) { const double d = (double)(xadj[v + 1] - xadj[v]); work += d * d; }
+    if (work > 4e9) return false;                // a dense constraint block: the clique expansion is not worth it
+    ga.reserve((size_t)std::min(work + (double)xadj[nvar], 2e9));
+  }
+  for (int64_t a = 0; a < nvar; a++) {
+    mark[a] = a;
+    for (int64_t p = xadj[a]; p < xadj[a + 1]; p++) {
+      const int64_t v = adj[p];
+      if (v < nvar) {
+        if (mark[v] != a) { mark[v] = a; ga.push_back(v); }
+      } else {
+        for (int64_t q = xadj[v]; q < xadj[v + 1]; q++) {
+          const int64_t b = adj[q];
+          if (mark[b] != a) { mark[b] = a; ga.push_back(b); }
+        }
+      }
+    }
+    gx[a + 1] = (int64_t)ga.size();
+  }
+  std::vector<int32_t> px;
+  if (!order_metis_nd(nvar, gx, ga, px, err)) return false;
+  perm.resize(n);
+  int64_t k = 0;
+  for (int64_t v = nvar; v < n; v++) perm[k++] = (int32_t)v;
+  for (int64_t i = 0; i < nvar; i++) perm[k++] = px[i];
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // Approximate minimum degree (Amestoy, Davis, Duff): quotient-graph elimination with
 // approximate external degrees, element absorption, mass elimination and hashed detection of

@@ -192,8 +192,10 @@ bool analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* cols1,
         int32_t i = S.Ai[p];
         if (i != j) { adj[cur[i]++] = j; adj[cur[j]++] = i; }
       }
-    bool ok = (opt.ordering == ORDER_AMD) ? order_amd(N, xadj, adj, perm0, S.error)
-                                          : order_metis_nd(N, xadj, adj, perm0, S.error);
+    bool ok;
+    if (opt.ordering == ORDER_AMD) ok = order_amd(N, xadj, adj, perm0, S.error);
+    else if (opt.ordering == ORDER_ND && order_kkt_compressed_nd(N, nvar, xadj, adj, perm0, S.error)) ok = true;
+    else ok = S.error.empty() && order_metis_nd(N, xadj, adj, perm0, S.error);
     if (!ok) return false;
   }
   S.t_order = now_s() - t_ord0;

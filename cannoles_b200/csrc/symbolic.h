@@ -19,6 +19,8 @@ enum Ordering : int {
   ORDER_NATURAL = 1,  // identity
   ORDER_USER = 2,     // caller-supplied permutation (perm[k] = 0-based original index of pivot k)
   ORDER_AMD = 3,      // approximate minimum degree (own implementation, ordering.cpp)
+  ORDER_ND_RAW = 4,   // nested dissection of the raw N-vertex graph (ORDER_ND dissects the compressed
+                      // x-vertex graph of a KKT matrix when the trailing block is diagonal)
 };
 
 struct SymbolicOptions {
@@ -101,6 +103,8 @@ bool analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* cols1,
 // orderings (ordering.cpp). adjacency = full symmetric pattern without diagonal.
 bool order_metis_nd(int64_t n, const std::vector<int64_t>& xadj, const std::vector<int64_t>& adj,
                     std::vector<int32_t>& perm, std::string& err);
+bool order_kkt_compressed_nd(int64_t n, int64_t nvar, const std::vector<int64_t>& xadj,
+                             const std::vector<int64_t>& adj, std::vector<int32_t>& perm, std::string& err);
 bool order_amd(int64_t n, const std::vector<int64_t>& xadj, const std::vector<int64_t>& adj,
                std::vector<int32_t>& perm, std::string& err);
 

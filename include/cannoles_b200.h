@@ -40,10 +40,12 @@ typedef struct b2_handle b2_handle;   /* one KKT system: symbolic plan + device 
 typedef struct b2b_handle b2b_handle; /* a batch of systems with one shared pattern      */
 
 /* orderings for b2_analyze / b2b_analyze */
-#define B2_ORDER_ND 0      /* nested dissection (default)                       */
+#define B2_ORDER_ND 0      /* nested dissection (default): of the compressed x-vertex graph (H + J'J
+                              pattern) when the trailing block of K is diagonal, as in a KKT matrix */
 #define B2_ORDER_NATURAL 1 /* identity                                          */
 #define B2_ORDER_USER 2    /* user_perm[k] = 0-based original index of pivot k  */
 #define B2_ORDER_AMD 3     /* approximate minimum degree                        */
+#define B2_ORDER_ND_RAW 4  /* nested dissection of the raw N-vertex graph       */
 
 typedef struct {
   int64_t N, nnz, nnzA;           /* order, COO entries, distinct upper-triangular positions   */
