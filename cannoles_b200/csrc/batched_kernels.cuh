@@ -141,19 +141,19 @@ __device__ __forceinline__ void ldlt8_regs(double (&g)[8][8], double (&rd)[8]) {
   }
 }
 
+// The work of ONE instance by one CTA (see the header of this file); `raw` = batched_smem_bytes of
+// shared memory, `cnt` = 4 ints of shared memory that hold the pivot-sign counts on return
+// (valid after the barrier the function ends its factorization part with).  v = the instance's COO
+// values, rho / -delta override the trailing segments when has_rho / has_del, bvec / dv = its
+// right-hand side / solution, Lb = its stored factor, c4 = its four output counters (or NULL).
+// Shared by k_batched and by the device-resident solver loop (nls_kernels.cuh).
 template <int NT>
-__global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const double* __restrict__ vals,
-                                                const double* __restrict__ rho_over,
-                                                const double* __restrict__ delta_over,
-                                                const uint8_t* __restrict__ active, double eig_tol,
-                                                long long* __restrict__ counts4, double* __restrict__ Lout,
-                                                const double* __restrict__ rhs, double* __restrict__ dout,
-                                                int flags) {
-  const int b = blockIdx.x;
-  if (b >= batch) return;
-  if (active && !active[b]) return;
+__device__ __forceinline__ void batched_instance(const BatchPlanDev& P, unsigned char* raw, int* cnt,
+                                                 const double* __restrict__ v, bool has_rho, double rho_b,
+                                                 bool has_del, double mdel_b, double eig_tol,
+                                                 long long* __restrict__ c4, double* __restrict__ Lb,
+                                                 const double* __restrict__ bvec, double* __restrict__ dv, int flags) {
   const int N = P.N;
-  B2_DYN_SMEM(raw);
   double* Pk = reinterpret_cast<double*>(raw);   // packed lower triangle
   double* xs = Pk + P.npacked;                   // N: solve vector
   double* lk = xs + N;                           // N: scratch
@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   int32_t* abase = reinterpret_cast<int32_t*>(dd + N);   // N: packed base of the contributing columns
   int32_t* rowmap = abase + N;                   // N: local row -> permuted index
   int32_t* cbm = rowmap + N;                     // N: copy of P.cbm
-  __shared__ int cnt[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;
   if (tid < 4) cnt[tid] = 0;
@@ -170,17 +169,15 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   B2_TICK(30);
 
   if (flags & BF_LOAD) {
-    const double* src = Lout + (size_t)b * P.npacked;
+    const double* src = Lb;
     for (int i = tid; i < P.npacked; i += NT) Pk[i] = src[i];
     __syncthreads();
   } else {
     // ---------------------------------------------------------------- assemble
     for (int i = tid; i < P.npacked; i += NT) Pk[i] = 0.0;
     __syncthreads();
-    const double* v = vals + (size_t)b * P.nnz;
     const int t_rho = P.nnz - P.nvar, t_del = t_rho - P.ncon;
-    const bool over = rho_over != nullptr || delta_over != nullptr;
-    const double rho_b = rho_over ? rho_over[b] : 0.0, mdel_b = delta_over ? -delta_over[b] : 0.0;
+    const bool over = has_rho || has_del;
     constexpr int U = 8;   // loads of U entries in flight per thread
     for (int t0 = tid; t0 < P.nnz; t0 += NT * U) {
       int dst[U];
@@ -197,8 +194,8 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
         if (dst[u] < 0) continue;
         double x = val[u];
         if (over) {
-          if (rho_over && t >= t_rho) x = rho_b;
-          else if (delta_over && t >= t_del && t < t_rho) x = mdel_b;
+          if (has_rho && t >= t_rho) x = rho_b;
+          else if (has_del && t >= t_del && t < t_rho) x = mdel_b;
         }
         Pk[dst[u]] = 0.0 + x;
       }
@@ -210,8 +207,8 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
         const int t = P.multi_coo[p];
         double x = v[t];
         if (over) {
-          if (rho_over && t >= t_rho) x = rho_b;
-          else if (delta_over && t >= t_del && t < t_rho) x = mdel_b;
+          if (has_rho && t >= t_rho) x = rho_b;
+          else if (has_del && t >= t_del && t < t_rho) x = mdel_b;
         }
         acc += x;
       }
@@ -352,10 +349,10 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
       if (neg) atomicAdd(&cnt[2], neg);
       if (brk) atomicAdd(&cnt[3], brk);
       __syncthreads();
-      if (tid < 4 && counts4) counts4[(size_t)b * 4 + tid] = cnt[tid];
+      if (tid < 4 && c4) c4[tid] = cnt[tid];
     }
     if (flags & BF_STORE) {
-      double* dst = Lout + (size_t)b * P.npacked;
+      double* dst = Lb;
       for (int i = tid; i < P.npacked; i += NT) dst[i] = Pk[i];
     }
     if ((flags & BF_SOLVE) && !(cnt[0] == P.nvar && cnt[1] == 0)) return;  // wrong inertia: no solve
@@ -363,7 +360,6 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   if (!(flags & BF_SOLVE)) return;
   B2_TICK(41);
   // ------------------------------------------------------------------ solve (factor in smem)
-  const double* bvec = rhs + (size_t)b * N;
   for (int k = tid; k < N; k += NT) xs[k] = bvec[P.perm[k]];
   __syncthreads();
   // forward: L y = b, level by level; a supernode first gathers the contributions of the
@@ -493,9 +489,27 @@ __global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const
   }
   B2_TICK(45);
   const double sign = (flags & BF_NEGATE) ? -1.0 : 1.0;
-  double* dv = dout + (size_t)b * N;
   for (int k = tid; k < N; k += NT) dv[P.perm[k]] = sign * xs[k];
   B2_TICK(42);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_batched(BatchPlanDev P, int batch, const double* __restrict__ vals,
+                                                const double* __restrict__ rho_over,
+                                                const double* __restrict__ delta_over,
+                                                const uint8_t* __restrict__ active, double eig_tol,
+                                                long long* __restrict__ counts4, double* __restrict__ Lout,
+                                                const double* __restrict__ rhs, double* __restrict__ dout,
+                                                int flags) {
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  if (active && !active[b]) return;
+  B2_DYN_SMEM(raw);
+  __shared__ int cnt[4];
+  batched_instance<NT>(P, raw, cnt, vals + (size_t)b * P.nnz, rho_over != nullptr, rho_over ? rho_over[b] : 0.0,
+                       delta_over != nullptr, delta_over ? -delta_over[b] : 0.0, eig_tol,
+                       counts4 ? counts4 + (size_t)b * 4 : nullptr, Lout ? Lout + (size_t)b * P.npacked : nullptr,
+                       rhs ? rhs + (size_t)b * P.N : nullptr, dout ? dout + (size_t)b * P.N : nullptr, flags);
 }
 
 }  // namespace b2
