@@ -30,6 +30,21 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class NLSParams(C.Structure):
+    """b2_nls_params_t"""
+    _fields_ = [(n, C.c_double) for n in (
+        "eig_tol", "delta_min", "kappa_dec", "kappa_inc", "kappa_largeinc", "rho0", "rho_max", "rho_min",
+        "gamma_A", "atol", "rtol", "Fatol", "Frtol", "delta_dec", "cgls_tol")] + [
+        (n, C.c_int32) for n in ("max_iter", "max_eval", "max_inner", "always_accept_extrapolation",
+                                 "use_initial_multiplier", "reserved")]
+
+
+class DenseNLS(C.Structure):
+    """b2_dense_nls_t"""
+    _fields_ = [(n, C.c_int64) for n in ("n", "m", "ncon", "shared_model")] + [
+        (n, pd) for n in ("At", "Bt", "Ct", "y", "e", "x0", "y0")]
+
+
 # every symbol include/cannoles_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
     "b2_last_error", "b2_version", "b2_device_count", "b2_analyze", "b2_factorize",
@@ -39,6 +54,8 @@ EXPORTS = [
     "b2b_analyze", "b2b_factorize", "b2b_refactorize_shift", "b2b_solve", "b2b_factorize_dev",
     "b2b_solve_dev", "b2b_factor_solve", "b2b_factor_solve_dev", "b2b_stats", "b2b_last_ms",
     "b2b_timer_start", "b2b_timer_stop", "b2b_get_perm", "b2b_get_d", "b2b_free",
+    "b2_nls_default_params", "b2b_nls_record_len", "b2b_nls_dense_solve_dev", "b2b_nls_dense_solve",
+    "b2b_nls_dense_submit", "b2b_nls_wait",
     "b2_dev_malloc", "b2_dev_free", "b2_dev_upload", "b2_dev_download", "b2_dev_sync",
     "b2_host_register", "b2_host_unregister",
     "b2_measure_dgemm", "b2_measure_hbm",
@@ -90,6 +107,15 @@ def bind_library(path: str):
         lib.b2b_get_perm.argtypes = [vp, p64]
         lib.b2b_get_d.argtypes = [vp, C.c_int64, pd]
         lib.b2b_free.argtypes = [vp]
+    if hasattr(lib, "b2b_nls_dense_solve"):
+        lib.b2_nls_default_params.argtypes = [C.POINTER(NLSParams)]
+        lib.b2_nls_default_params.restype = None
+        lib.b2b_nls_record_len.argtypes = [vp]
+        lib.b2b_nls_record_len.restype = C.c_int64
+        lib.b2b_nls_dense_solve_dev.argtypes = [vp, C.POINTER(DenseNLS), C.c_int64, C.POINTER(NLSParams), vp, vp]
+        lib.b2b_nls_dense_solve.argtypes = [vp, C.POINTER(DenseNLS), C.c_int64, C.POINTER(NLSParams), pd, C.c_int64]
+        lib.b2b_nls_dense_submit.argtypes = [vp, C.POINTER(DenseNLS), C.c_int64, C.POINTER(NLSParams), vp, C.c_int]
+        lib.b2b_nls_wait.argtypes = [vp]
     if hasattr(lib, "b2_dev_malloc"):
         lib.b2_dev_malloc.argtypes = [C.POINTER(vp), C.c_size_t]
         lib.b2_dev_free.argtypes = [vp]

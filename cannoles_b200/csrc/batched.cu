@@ -10,6 +10,7 @@
 #include "../../include/cannoles_b200.h"
 #include "b2_cuda.h"
 #include "batched_kernels.cuh"
+#include "nls_kernels.cuh"
 #include "symbolic.h"
 
 namespace b2 {
@@ -36,6 +37,40 @@ struct BatchEngine {
   double last_ms = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t tev[2] = {nullptr, nullptr};
+  // device-resident solver loop (nls_kernels.cuh)
+  static constexpr int NLS_SLOTS = 3;          // chunk kernels in flight (one stream each)
+  int nsm = 0, nls_smem = 0;
+  bool nls_ready = false;
+  cudaStream_t nls_stream[NLS_SLOTS] = {nullptr, nullptr, nullptr}, copy_stream = nullptr;
+  cudaEvent_t nls_done[NLS_SLOTS] = {nullptr, nullptr, nullptr}, nls_start = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  double* nls_scr[NLS_SLOTS] = {nullptr, nullptr, nullptr};   // per slot: nsm x nnz COO values
+  int* nls_tickets = nullptr;
+  int nls_ntickets = 0;
+  double* nls_rec = nullptr;                   // batch x record
+  double* nls_model[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // At Bt Ct y e x0 (host-data verb)
+  size_t nls_model_cap[6] = {0, 0, 0, 0, 0, 0};
+  int nls_launches = 0;
+  int nls_init(int n, int m, int nc);
+  // asynchronous submissions (b2b_nls_dense_submit): every submission runs start to end on ONE lane
+  // (its H2D, its kernel, its D2H in stream order, own model buffers / scratch / ticket), successive
+  // submissions on successive lanes, so that batches overlap: the copy engines of one with the SMs of
+  // another, and the SMs a batch leaves idle while its slowest instance finishes with the next batch
+  static constexpr int NLS_LANES = 24;
+  struct NlsLane {
+    cudaStream_t q = nullptr;
+    cudaEvent_t done = nullptr;
+    double* scr = nullptr;
+    int* ticket = nullptr;
+    double* model[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    double* rec = nullptr;
+    size_t rec_cap = 0;
+    bool pending = false;
+  };
+  NlsLane lanes[NLS_LANES];
+  int next_lane = 0;
+  cudaEvent_t lane_start = nullptr;
 
   template <typename T>
   int up(const std::vector<T>& v, const T** out) {
@@ -178,6 +213,16 @@ void BatchEngine::destroy() {
   if (h_counts) cudaFreeHost(h_counts);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   for (auto& e : tev) if (e) cudaEventDestroy(e);
+  for (auto& e : nls_done) if (e) cudaEventDestroy(e);
+  for (auto& e : chunk_ev) if (e) cudaEventDestroy(e);
+  if (nls_start) cudaEventDestroy(nls_start);
+  if (lane_start) cudaEventDestroy(lane_start);
+  for (auto& L : lanes) {
+    if (L.done) cudaEventDestroy(L.done);
+    if (L.q) cudaStreamDestroy(L.q);
+  }
+  for (auto& q : nls_stream) if (q) cudaStreamDestroy(q);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -208,6 +253,50 @@ int BatchEngine::fetch_counts(int64_t* npos, int64_t* nzero, int64_t* nneg, int3
   return 0;
 }
 
+// Buffers, streams and the shared-memory opt-in of k_nls_dense; idempotent.
+int BatchEngine::nls_init(int n, int m, int nc) {
+  if (nls_ready) return 0;
+  const int N = (int)sym.N;
+  if (n != sym.nvar || m != sym.nequ || nc != sym.ncon) {
+    snprintf(g_last_error, sizeof(g_last_error), "b2b_nls: model dimensions (%d, %d, %d) differ from the analysed KKT "
+             "layout (%lld, %lld, %lld)", n, m, nc, (long long)sym.nvar, (long long)sym.nequ, (long long)sym.ncon);
+    return -1;
+  }
+  const long long nh = (long long)n * (n + 1) / 2;
+  const long long expect = nh + (nc > 0 ? nh : 0) + (long long)n * m + (long long)n * nc + m + nc + n;
+  if (expect != sym.nnz || !sym.shift_ok) {
+    snprintf(g_last_error, sizeof(g_last_error), "b2b_nls: the analysed COO layout (nnz = %lld) is not the Newton-mode "
+             "layout of a dense model with these dimensions (nnz = %lld, SURVEY App. B)", (long long)sym.nnz, expect);
+    return -1;
+  }
+  if (m > BATCH_NT || n > BATCH_NT || (nc > BATCH_NT)) {
+    snprintf(g_last_error, sizeof(g_last_error), "b2b_nls: n, m, ncon must not exceed %d", BATCH_NT);
+    return -1;
+  }
+  nls_smem = (int)(((batched_smem_bytes(N, plan.npacked) + 15) & ~(size_t)15) +
+                   nls_state_doubles(n, m, nc, BATCH_NT) * sizeof(double));
+  if (nls_smem > 227 * 1024) {
+    snprintf(g_last_error, sizeof(g_last_error), "b2b_nls: %d bytes of shared memory per instance (> 227 KB)", nls_smem);
+    return -1;
+  }
+  B2_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  nsm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  for (auto& q : nls_stream) B2_CUDA_OK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+  B2_CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  for (auto& e : nls_done) B2_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  B2_CUDA_OK(cudaEventCreateWithFlags(&nls_start, cudaEventDisableTiming));
+  for (auto& p : nls_scr)
+    if (alloc(&p, (size_t)nsm * sym.nnz)) return -1;
+  nls_ntickets = 1024;
+  if (alloc(&nls_tickets, (size_t)nls_ntickets)) return -1;
+  if (alloc(&nls_rec, (size_t)batch * (NLS_REC_HEAD + n + nc))) return -1;
+  B2_CUDA_OK(cudaFuncSetAttribute(k_nls_dense<BATCH_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, nls_smem));
+  nls_ready = true;
+  return 0;
+}
+
 }  // namespace b2
 
 struct b2b_handle {
@@ -223,7 +312,9 @@ int failb(const char* msg) {
 
 #ifdef B2_TIMING
 extern "C" int b2b_debug_clocks(long long* out64) {
-  return cudaMemcpyFromSymbol(out64, b2::b2_dbg, 64 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+  if (cudaMemcpyFromSymbol(out64, b2::b2_dbg, 64 * sizeof(long long)) != cudaSuccess) return -1;
+  static const long long zero[64] = {0};
+  return cudaMemcpyToSymbol(b2::b2_dbg, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;   // read and clear
 }
 #endif
 
@@ -464,6 +555,226 @@ int b2b_stats(const b2b_handle* h, b2_stats_t* o) {
   o->launches_factor = 1; o->launches_solve = 1;
   o->flops = S.flops; o->flops_store = S.flops_store; o->t_order = S.t_order; o->t_symbolic = S.t_symbolic;
   o->t_plan = h->eng.t_plan; o->bytes_device = h->eng.bytes_device;
+  return 0;
+}
+
+/* ---- device-resident CaNNOLeS loop for batches of small dense instances (nls_kernels.cuh) ---- */
+void b2_nls_default_params(b2_nls_params_t* p) {   /* update!(params, eps(Float64)) : src/CaNNOLeS.jl:48-62 */
+  if (!p) return;
+  const double e = 2.220446049250313e-16;
+  p->eig_tol = e; p->delta_min = std::sqrt(e); p->kappa_dec = 1.0 / 3.0; p->kappa_inc = 8.0; p->kappa_largeinc = 100.0;
+  p->rho0 = std::pow(e, 1.0 / 3.0);   /* eps^T(1/3): pow, not cbrt -- they differ in the last bits and rho0 reaches the pivots */
+  p->rho_max = std::pow(e, -2.0); p->rho_min = std::sqrt(e); p->gamma_A = std::pow(e, 0.25);
+  p->atol = p->rtol = p->Fatol = std::sqrt(e); p->Frtol = e; p->delta_dec = 0.1; p->cgls_tol = std::sqrt(e);
+  p->max_iter = -1; p->max_eval = 100000; p->max_inner = 10000; p->always_accept_extrapolation = 0;
+  p->use_initial_multiplier = 0; p->reserved = 0;
+}
+
+int64_t b2b_nls_record_len(const b2b_handle* h) {
+  if (!h) return -1;
+  return b2::NLS_REC_HEAD + h->eng.sym.nvar + h->eng.sym.ncon;
+}
+
+namespace {
+int nls_model_dev(const b2_dense_nls_t* md, b2::DenseNlsModel* M) {
+  M->n = (int)md->n; M->m = (int)md->m; M->ncon = (int)md->ncon;
+  const bool sh = md->shared_model != 0;
+  M->stride_A = sh ? 0 : md->n * md->m; M->stride_C = sh ? 0 : md->n * md->ncon;
+  M->stride_y = sh ? 0 : md->m; M->stride_e = sh ? 0 : md->ncon; M->stride_x0 = md->n;
+  M->At = md->At; M->Bt = md->Bt; M->Ct = md->Ct; M->y = md->y; M->e = md->e; M->x0 = md->x0; M->y0 = md->y0;
+  return 0;
+}
+b2::NlsParams nls_params(const b2_nls_params_t* p) {
+  b2::NlsParams q;
+  q.eig_tol = p->eig_tol; q.delta_min = p->delta_min; q.kappa_dec = p->kappa_dec; q.kappa_inc = p->kappa_inc;
+  q.kappa_largeinc = p->kappa_largeinc; q.rho0 = p->rho0; q.rho_max = p->rho_max; q.rho_min = p->rho_min;
+  q.gamma_A = p->gamma_A; q.atol = p->atol; q.rtol = p->rtol; q.Fatol = p->Fatol; q.Frtol = p->Frtol;
+  q.delta_dec = p->delta_dec; q.cgls_tol = p->cgls_tol; q.eps2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+  q.max_iter = p->max_iter; q.max_eval = p->max_eval; q.max_inner = p->max_inner;
+  q.always_accept_extrapolation = p->always_accept_extrapolation; q.use_initial_multiplier = p->use_initial_multiplier;
+  return q;
+}
+}  // namespace
+
+/* All pointers of *model_dev and d_records / d_dbg_vals are DEVICE pointers; instances 0 .. count-1. */
+int b2b_nls_dense_solve_dev(b2b_handle* h, const b2_dense_nls_t* model_dev, int64_t count,
+                            const b2_nls_params_t* params, double* d_records, double* d_dbg_vals) {
+  if (!h || !model_dev || !params || !d_records) return failb("b2b_nls_dense_solve_dev: NULL argument");
+  b2::BatchEngine& E = h->eng;
+  if (count <= 0 || count > E.batch) return failb("b2b_nls_dense_solve_dev: count must be in 1 .. batch");
+  if (E.nls_init((int)model_dev->n, (int)model_dev->m, (int)model_dev->ncon)) return -1;
+  B2_CUDA_OK(cudaSetDevice(E.device));
+  b2::DenseNlsModel M;
+  nls_model_dev(model_dev, &M);
+  const b2::NlsParams prm = nls_params(params);
+  const int grid = (int)std::min<int64_t>(count, E.nsm);
+  B2_CUDA_OK(cudaMemsetAsync(E.nls_tickets, 0, sizeof(int), E.stream));
+  B2_CUDA_OK(cudaEventRecord(E.ev[0], E.stream));
+  B2_LAUNCH(b2::k_nls_dense<b2::BATCH_NT>, (unsigned)grid, b2::BATCH_NT, E.nls_smem, E.stream, E.plan, M, prm, 0,
+            (int)count, E.nls_tickets, E.nls_scr[0], d_records, (int)b2b_nls_record_len(h), d_dbg_vals);
+  B2_CUDA_OK(cudaGetLastError());
+  B2_CUDA_OK(cudaEventRecord(E.ev[1], E.stream));
+  B2_CUDA_OK(cudaStreamSynchronize(E.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, E.ev[0], E.ev[1]);
+  E.last_ms = ms;
+  E.nls_launches = 1;
+  return 0;
+}
+
+/* HOST model arrays (pin them with b2_host_register for full PCIe speed) and host records: the
+ * model travels in chunks of `chunk` instances on a copy stream while the chunks that have arrived
+ * are being solved (up to three chunk kernels in flight so that the tail of one chunk overlaps the
+ * head of the next); records come back per chunk.  chunk <= 0 picks a size. */
+int b2b_nls_dense_solve(b2b_handle* h, const b2_dense_nls_t* model_host, int64_t count,
+                        const b2_nls_params_t* params, double* records, int64_t chunk) {
+  if (!h || !model_host || !params || !records) return failb("b2b_nls_dense_solve: NULL argument");
+  b2::BatchEngine& E = h->eng;
+  if (count <= 0 || count > E.batch) return failb("b2b_nls_dense_solve: count must be in 1 .. batch");
+  const b2_dense_nls_t& mh = *model_host;
+  if (E.nls_init((int)mh.n, (int)mh.m, (int)mh.ncon)) return -1;
+  B2_CUDA_OK(cudaSetDevice(E.device));
+  const bool sh = mh.shared_model != 0;
+  const size_t per[6] = {(size_t)(mh.n * mh.m), (size_t)(mh.n * mh.m), (size_t)(mh.n * mh.ncon), (size_t)mh.m,
+                         (size_t)mh.ncon, (size_t)mh.n};
+  const double* src[6] = {mh.At, mh.Bt, mh.Ct, mh.y, mh.e, mh.x0};
+  for (int a = 0; a < 6; a++) {
+    if (!src[a] && per[a]) return failb("b2b_nls_dense_solve: NULL model array");
+    const size_t need = per[a] * (size_t)((sh && a < 5) ? 1 : count);
+    if (E.nls_model_cap[a] < need) {
+      if (E.alloc(&E.nls_model[a], need)) return -1;   // (an outgrown buffer stays owned by dev_ptrs until b2b_free)
+      E.nls_model_cap[a] = need;
+    }
+  }
+  if (chunk <= 0) chunk = std::max<int64_t>(2 * E.nsm, (count + 15) / 16);
+  const int nchunk = (int)((count + chunk - 1) / chunk);
+  if (nchunk > E.nls_ntickets) return failb("b2b_nls_dense_solve: too many chunks");
+  while ((int)E.chunk_ev.size() < nchunk) {
+    cudaEvent_t e;
+    B2_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    E.chunk_ev.push_back(e);
+  }
+  b2_dense_nls_t md = mh;
+  md.At = E.nls_model[0]; md.Bt = E.nls_model[1]; md.Ct = E.nls_model[2]; md.y = E.nls_model[3];
+  md.e = E.nls_model[4]; md.x0 = E.nls_model[5]; md.y0 = nullptr;
+  if (mh.y0) return failb("b2b_nls_dense_solve: y0 is only supported by the _dev verb");
+  b2::DenseNlsModel M;
+  nls_model_dev(&md, &M);
+  const b2::NlsParams prm = nls_params(params);
+  const int rl = (int)b2b_nls_record_len(h);
+  B2_CUDA_OK(cudaMemsetAsync(E.nls_tickets, 0, sizeof(int) * nchunk, E.stream));
+  B2_CUDA_OK(cudaEventRecord(E.ev[0], E.stream));
+  B2_CUDA_OK(cudaEventRecord(E.nls_start, E.stream));
+  B2_CUDA_OK(cudaStreamWaitEvent(E.copy_stream, E.nls_start, 0));
+  for (auto& q : E.nls_stream) B2_CUDA_OK(cudaStreamWaitEvent(q, E.nls_start, 0));
+  if (sh)
+    for (int a = 0; a < 5; a++)
+      B2_CUDA_OK(cudaMemcpyAsync(E.nls_model[a], src[a], per[a] * sizeof(double), cudaMemcpyHostToDevice, E.copy_stream));
+  for (int c = 0; c < nchunk; c++) {
+    const int64_t c0 = (int64_t)c * chunk, cn = std::min<int64_t>(chunk, count - c0);
+    for (int a = sh ? 5 : 0; a < 6; a++)
+      B2_CUDA_OK(cudaMemcpyAsync(E.nls_model[a] + (size_t)c0 * per[a], src[a] + (size_t)c0 * per[a],
+                                 (size_t)cn * per[a] * sizeof(double), cudaMemcpyHostToDevice, E.copy_stream));
+    B2_CUDA_OK(cudaEventRecord(E.chunk_ev[c], E.copy_stream));
+    cudaStream_t q = E.nls_stream[c % b2::BatchEngine::NLS_SLOTS];
+    B2_CUDA_OK(cudaStreamWaitEvent(q, E.chunk_ev[c], 0));
+    const int grid = (int)std::min<int64_t>(cn, E.nsm);
+    B2_LAUNCH(b2::k_nls_dense<b2::BATCH_NT>, (unsigned)grid, b2::BATCH_NT, E.nls_smem, q, E.plan, M, prm, (int)c0, (int)cn,
+              E.nls_tickets + c, E.nls_scr[c % b2::BatchEngine::NLS_SLOTS], E.nls_rec, rl, (double*)nullptr);
+    B2_CUDA_OK(cudaGetLastError());
+    B2_CUDA_OK(cudaMemcpyAsync(records + (size_t)c0 * rl, E.nls_rec + (size_t)c0 * rl, (size_t)cn * rl * sizeof(double),
+                               cudaMemcpyDeviceToHost, q));
+  }
+  for (int q = 0; q < b2::BatchEngine::NLS_SLOTS; q++) {
+    B2_CUDA_OK(cudaEventRecord(E.nls_done[q], E.nls_stream[q]));
+    B2_CUDA_OK(cudaStreamWaitEvent(E.stream, E.nls_done[q], 0));
+  }
+  B2_CUDA_OK(cudaEventRecord(E.ev[1], E.stream));
+  B2_CUDA_OK(cudaStreamSynchronize(E.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, E.ev[0], E.ev[1]);
+  E.last_ms = ms;
+  E.nls_launches = nchunk;
+  return 0;
+}
+
+/* Asynchronous form: queues one batch (its upload, its solve, its download) on the next of the
+ * handle's lanes and returns; b2b_nls_wait blocks until every queued batch is complete.  Batches in
+ * flight overlap each other (PCIe of one with the SMs of another; the SMs one batch leaves idle
+ * while its slowest instance finishes take the next batch).  where = 0: *model and records are HOST
+ * memory (pinned for true asynchrony); where = 1: both are DEVICE memory.  The caller keeps model
+ * arrays and records alive and untouched until b2b_nls_wait returns. */
+int b2b_nls_dense_submit(b2b_handle* h, const b2_dense_nls_t* model, int64_t count, const b2_nls_params_t* params,
+                         double* records, int where) {
+  if (!h || !model || !params || !records) return failb("b2b_nls_dense_submit: NULL argument");
+  b2::BatchEngine& E = h->eng;
+  if (count <= 0 || count > E.batch) return failb("b2b_nls_dense_submit: count must be in 1 .. batch");
+  const b2_dense_nls_t& mh = *model;
+  if (E.nls_init((int)mh.n, (int)mh.m, (int)mh.ncon)) return -1;
+  B2_CUDA_OK(cudaSetDevice(E.device));
+  b2::BatchEngine::NlsLane& L = E.lanes[E.next_lane];
+  E.next_lane = (E.next_lane + 1) % b2::BatchEngine::NLS_LANES;
+  if (!L.q) {
+    B2_CUDA_OK(cudaStreamCreateWithFlags(&L.q, cudaStreamNonBlocking));
+    B2_CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    if (E.alloc(&L.scr, (size_t)E.nsm * E.sym.nnz) || E.alloc(&L.ticket, 1)) return -1;
+  }
+  if (!E.lane_start) B2_CUDA_OK(cudaEventCreateWithFlags(&E.lane_start, cudaEventDisableTiming));
+  const int rl = (int)b2b_nls_record_len(h);
+  const bool sh = mh.shared_model != 0;
+  b2_dense_nls_t md = mh;
+  double* drec = records;
+  // the lane starts after whatever the caller queued on the handle's main stream (b2b_timer_start)
+  B2_CUDA_OK(cudaEventRecord(E.lane_start, E.stream));
+  B2_CUDA_OK(cudaStreamWaitEvent(L.q, E.lane_start, 0));
+  if (where == 0) {
+    if (mh.y0) return failb("b2b_nls_dense_submit: y0 needs device-resident data (where = 1)");
+    const size_t per[6] = {(size_t)(mh.n * mh.m), (size_t)(mh.n * mh.m), (size_t)(mh.n * mh.ncon), (size_t)mh.m,
+                           (size_t)mh.ncon, (size_t)mh.n};
+    const double* src[6] = {mh.At, mh.Bt, mh.Ct, mh.y, mh.e, mh.x0};
+    for (int a = 0; a < 6; a++) {
+      if (!src[a] && per[a]) return failb("b2b_nls_dense_submit: NULL model array");
+      const size_t need = per[a] * (size_t)((sh && a < 5) ? 1 : count);
+      if (L.cap[a] < need) {
+        if (E.alloc(&L.model[a], need)) return -1;
+        L.cap[a] = need;
+      }
+      B2_CUDA_OK(cudaMemcpyAsync(L.model[a], src[a], need * sizeof(double), cudaMemcpyHostToDevice, L.q));
+    }
+    if (L.rec_cap < (size_t)count * rl) {
+      if (E.alloc(&L.rec, (size_t)count * rl)) return -1;
+      L.rec_cap = (size_t)count * rl;
+    }
+    md.At = L.model[0]; md.Bt = L.model[1]; md.Ct = L.model[2]; md.y = L.model[3]; md.e = L.model[4];
+    md.x0 = L.model[5]; md.y0 = nullptr;
+    drec = L.rec;
+  }
+  b2::DenseNlsModel M;
+  nls_model_dev(&md, &M);
+  const b2::NlsParams prm = nls_params(params);
+  const int grid = (int)std::min<int64_t>(count, E.nsm);
+  B2_CUDA_OK(cudaMemsetAsync(L.ticket, 0, sizeof(int), L.q));
+  B2_LAUNCH(b2::k_nls_dense<b2::BATCH_NT>, (unsigned)grid, b2::BATCH_NT, E.nls_smem, L.q, E.plan, M, prm, 0, (int)count,
+            L.ticket, L.scr, drec, rl, (double*)nullptr);
+  B2_CUDA_OK(cudaGetLastError());
+  if (where == 0)
+    B2_CUDA_OK(cudaMemcpyAsync(records, L.rec, (size_t)count * rl * sizeof(double), cudaMemcpyDeviceToHost, L.q));
+  B2_CUDA_OK(cudaEventRecord(L.done, L.q));
+  L.pending = true;
+  E.nls_launches++;
+  return 0;
+}
+
+int b2b_nls_wait(b2b_handle* h) {
+  if (!h) return failb("b2b_nls_wait: NULL handle");
+  b2::BatchEngine& E = h->eng;
+  B2_CUDA_OK(cudaSetDevice(E.device));
+  for (auto& L : E.lanes)
+    if (L.pending) {
+      B2_CUDA_OK(cudaStreamWaitEvent(E.stream, L.done, 0));   // so that b2b_timer_stop brackets the lanes
+      L.pending = false;
+    }
+  B2_CUDA_OK(cudaStreamSynchronize(E.stream));
   return 0;
 }
 

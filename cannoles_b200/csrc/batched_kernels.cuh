@@ -47,7 +47,7 @@ struct BatchPlanDev {
 };
 
 // shared memory of k_batched, in bytes, for a system of order N
-inline size_t batched_smem_bytes(int N, int64_t npacked) {
+__host__ __device__ inline size_t batched_smem_bytes(int N, int64_t npacked) {
   return ((size_t)npacked + 11 * (size_t)N) * sizeof(double) + 3 * (size_t)N * sizeof(int32_t);
 }
 
@@ -149,10 +149,12 @@ __device__ __forceinline__ void ldlt8_regs(double (&g)[8][8], double (&rd)[8]) {
 // Shared by k_batched and by the device-resident solver loop (nls_kernels.cuh).
 template <int NT>
 __device__ __forceinline__ void batched_instance(const BatchPlanDev& P, unsigned char* raw, int* cnt,
-                                                 const double* __restrict__ v, bool has_rho, double rho_b,
+                                                 const double* v, bool has_rho, double rho_b,
                                                  bool has_del, double mdel_b, double eig_tol,
-                                                 long long* __restrict__ c4, double* __restrict__ Lb,
-                                                 const double* __restrict__ bvec, double* __restrict__ dv, int flags) {
+                                                 long long* c4, double* Lb,
+                                                 const double* bvec, double* dv, int flags) {
+  // (no __restrict__ here: the solver loop writes v / bvec from the same kernel, and bvec / dv may be
+  // shared memory; k_batched's own parameters keep the qualifier)
   const int N = P.N;
   double* Pk = reinterpret_cast<double*>(raw);   // packed lower triangle
   double* xs = Pk + P.npacked;                   // N: solve vector

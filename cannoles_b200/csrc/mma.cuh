@@ -8,9 +8,13 @@ namespace b2 {
 __device__ long long b2_dbg[64];
 #define B2_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] = clock64(); } while (0)
 #define B2_ACC(i, t0) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] += clock64() - (t0); } while (0)
+#define B2_ACC1(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2_dbg[i] += 1; } while (0)
+#define B2_T0(name) const long long name = clock64()
 #else
 #define B2_TICK(i)
 #define B2_ACC(i, t0)
+#define B2_ACC1(i)
+#define B2_T0(name)
 #endif
 
 // D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores (PTX mma.m8n8k4.f64 = SASS DMMA).

@@ -176,6 +176,49 @@ int b2b_timer_start(b2b_handle* h);
 int b2b_timer_stop(b2b_handle* h, double* ms);
 int b2b_get_perm(const b2b_handle* h, int64_t* perm0);
 int b2b_get_d(b2b_handle* h, int64_t instance, double* d); /* pivots of one stored factor */
+
+/* ---- device-resident CaNNOLeS loop for a batch of small dense instances -----------------
+ * Replaces, per instance and with no host round trip, what `solve!` does around the linear
+ * solver (src/CaNNOLeS.jl:418-864): prepare_newton_system! (:947-981),
+ * newton_system! (:1008-1052), the trial-point products and norms (:508, 521-525, 722-732,
+ * 753-755; N2), the CGLS multiplier estimate (:513, 872-897; N3), the extrapolation step, the
+ * line search (:1054-1112) and get_status.  The handle is the one b2b_analyze made for the
+ * Newton-mode KKT layout of the model.  Model: DenseBatchNLS,
+ *   F(x) = A x + 0.1 sin(B x) - y,  c(x) = C x + 0.05 (x.x)[0:ncon] - e = 0,
+ * A, B (m x n) and C (ncon x n) stored column-major per instance. */
+typedef struct {
+  double eig_tol, delta_min, kappa_dec, kappa_inc, kappa_largeinc, rho0, rho_max, rho_min, gamma_A; /* ParamCaNNOLeS :36-87 */
+  double atol, rtol, Fatol, Frtol, delta_dec;   /* keyword arguments of solve! (:418-436) */
+  double cgls_tol;                              /* Krylov.cgls atol = rtol */
+  int32_t max_iter, max_eval, max_inner, always_accept_extrapolation, use_initial_multiplier, reserved;
+} b2_nls_params_t;
+void b2_nls_default_params(b2_nls_params_t* p);
+typedef struct {
+  int64_t n, m, ncon;
+  int64_t shared_model;   /* != 0: one (A, B, C, y, e) for all instances, only x0 varies (multi-start) */
+  const double *At, *Bt;  /* per instance n x m:    At[j * m + i] = A[i][j] */
+  const double* Ct;       /* per instance n x ncon: Ct[j * ncon + k] = C[k][j] */
+  const double *y, *e;    /* m, ncon */
+  const double* x0;       /* n per instance (always per instance) */
+  const double* y0;       /* ncon per instance or NULL (_dev verb only; used with use_initial_multiplier) */
+} b2_dense_nls_t;
+/* doubles per instance record: status, iter, nfact, nlinsolve, nbk, neval_residual, neval_cons,
+ * objective, primal_feas, dual_feas, rho, delta, x[n], lambda[ncon].  status: 0 unknown, 1 first_order,
+ * 2 small_residual, 3 stalled, 4 exception, 5 max_eval, 6 max_time, 7 max_iter; 8 / 9 / 10 = the
+ * errors the reference throws (NaN at x0 :484-487, Dphi >= 0 :1085, alpha too small :1097) */
+int64_t b2b_nls_record_len(const b2b_handle* h);
+int b2b_nls_dense_solve_dev(b2b_handle* h, const b2_dense_nls_t* model_dev, int64_t count,
+                            const b2_nls_params_t* params, double* d_records, double* d_dbg_vals);
+int b2b_nls_dense_solve(b2b_handle* h, const b2_dense_nls_t* model_host, int64_t count,
+                        const b2_nls_params_t* params, double* records, int64_t chunk);
+/* Asynchronous form: queue one batch (upload, solve, download in stream order on one of the
+ * handle's 24 lanes) and return; b2b_nls_wait blocks until every queued batch is complete.
+ * Batches in flight overlap: PCIe of one with the SMs of another, and the SMs a batch leaves idle
+ * while its slowest instance finishes are taken by the next batch.  where = 0: *model and records
+ * are host memory (pin them); where = 1: device memory.  Arrays stay untouched until the wait. */
+int b2b_nls_dense_submit(b2b_handle* h, const b2_dense_nls_t* model, int64_t count,
+                         const b2_nls_params_t* params, double* records, int where);
+int b2b_nls_wait(b2b_handle* h);
 int b2b_free(b2b_handle* h);
 
 /* device utilities used by bench.py / tests (plain cudaMalloc / cudaMemcpy wrappers so that

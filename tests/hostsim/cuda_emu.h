@@ -18,6 +18,8 @@
 #include <algorithm>
 using std::min;
 using std::max;
+using std::isfinite;
+using std::isnan;
 
 #define __global__
 #define __device__
