@@ -130,9 +130,17 @@ def test_reference_known_answers_through_the_gpu_backend(ctor):
         ec.assert_same_run(stb, sto)
     stb, sto = ec.run_cannoles_both(MGH01CON(), ctor)
     ec.assert_same_run(stb, sto)
+    # HS6 (test/runtests.jl:116-138, atol 1e-6 there): the last Newton systems have delta = 1e-5 and the
+    # un-refined reference solve (LDLFactorizations does no refinement) leaves an error of ~2e-8 in x under the
+    # elimination order in use; the backend's adaptive refinement lands on [1, 1] to the last bit.  Same
+    # iteration counts, and the two final points agree within the reference's own solve error
     stb, sto = ec.run_cannoles_both(hs6(), ctor)
     assert stb.status == "first_order" and np.allclose(stb.solution, [1, 1], atol=1e-6)
-    ec.assert_same_run(stb, sto)
+    ec.assert_same_run(stb, sto, rtol=1e-7)
+    assert np.linalg.norm(stb.solution - 1.0) <= np.linalg.norm(sto.solution - 1.0) + 1e-12
+    # without refinement the backend does the reference's arithmetic: 1e-8 holds
+    stb0, sto0 = ec.run_cannoles_both(hs6(), functools.partial(ctor, refine_steps=0))
+    ec.assert_same_run(stb0, sto0, rtol=1e-8)
 
 
 def test_cannoles_on_a_config_slice_matches_oracle(ctor):
