@@ -113,11 +113,81 @@ __device__ __forceinline__ bool cta_nonfinite(const double* a, int len) {   // c
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA (bulk asynchronous copy, global -> shared, completion on an mbarrier): the model matrices A and
+// B of the instance (n columns of m doubles each, 2 x 64 KB for config 5) are staged into the shared
+// memory of the packed KKT triangle while that triangle is dead -- from the end of a solve to the
+// next assembly, which is exactly when the model is evaluated (trial residual, J'v products, the
+// Jacobian and Hessian segments of the next system).  One warp issues one cp.async.bulk per column
+// (a padded column stride keeps the FP64 tensor-core fragment loads of the Hessian conflict-free),
+// nobody holds the data in registers on the way, and every evaluator reads shared memory instead of
+// going back to L2 five or six times per Newton system.
+#ifndef B2_EMULATE
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // model evaluators (all CTA-collective; they end with a barrier)
 struct DenseInst {
   int n, m, nc;
-  const double *At, *Bt, *Ct, *y, *e;
+  const double *At, *Bt, *Ct, *y, *e;   // the instance's arrays in HBM
+  const double *Aw, *Bw;                // A and B as the evaluators read them: staged in shared memory (or = At, Bt)
+  int ldw;                              // column stride of Aw / Bw
 };
+
+// Stage A and B of the instance into `dstA` / `dstB` (shared memory, column stride lds).  CTA-collective.
+// `phase` is the mbarrier parity of this use (the caller flips it after every call).
+template <int NT>
+__device__ __forceinline__ bool dn_stage_model(DenseInst& I, double* dstA, double* dstB, int lds,
+                                               unsigned long long* bar, uint32_t phase) {
+  const int n = I.n, m = I.m, tid = threadIdx.x;
+  __syncthreads();                      // every generic-proxy access to the destination is complete
+#ifndef B2_EMULATE
+  const bool tma_ok = (m % 2 == 0) && (lds % 2 == 0) && ((reinterpret_cast<uintptr_t>(I.At) | reinterpret_cast<uintptr_t>(I.Bt)) % 16 == 0);
+  if (tma_ok) {
+    if (tid < 32) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (tid == 0) mbar_expect_tx(bar, (uint32_t)(2 * n * m * sizeof(double)));
+      __syncwarp();
+      for (int j = tid; j < n; j += 32) {
+        tma_bulk_g2s(dstA + (size_t)j * lds, I.At + (size_t)j * m, (uint32_t)(m * sizeof(double)), bar);
+        tma_bulk_g2s(dstB + (size_t)j * lds, I.Bt + (size_t)j * m, (uint32_t)(m * sizeof(double)), bar);
+      }
+    }
+    mbar_wait(bar, phase);
+    I.Aw = dstA; I.Bw = dstB; I.ldw = lds;
+    return true;                        // the mbarrier went through one phase
+  }
+#endif
+  {
+    for (int q = tid; q < n * m; q += NT) {
+      const int j = q / m, i = q - j * m;
+      dstA[(size_t)j * lds + i] = I.At[q];
+      dstB[(size_t)j * lds + i] = I.Bt[q];
+    }
+    __syncthreads();
+  }
+  I.Aw = dstA; I.Bw = dstB; I.ldw = lds;
+  return false;
+}
 
 // Fx = A x + 0.1 sin(B x) - y; sn = sin(B x), cs = cos(B x) are kept: they define J(x) and H(x)
 template <int NT>
@@ -131,8 +201,8 @@ __device__ __forceinline__ void dn_residual(const DenseInst& I, const double* x,
 #pragma unroll 4
     for (int j = p; j < n; j += npart) {
       const double xj = x[j];
-      sa += I.At[(size_t)j * m + i] * xj;
-      sb += I.Bt[(size_t)j * m + i] * xj;
+      sa += I.Aw[(size_t)j * I.ldw + i] * xj;
+      sb += I.Bw[(size_t)j * I.ldw + i] * xj;
     }
   }
   scr[tid] = sa;
@@ -175,8 +245,8 @@ template <int NT>
 __device__ __forceinline__ void dn_jtprod_res(const DenseInst& I, const double* cs, const double* v, double* out) {
   const int m = I.m, n = I.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int j = warp; j < n; j += NT / 32) {
-    const double* a = I.At + (size_t)j * m;
-    const double* b = I.Bt + (size_t)j * m;
+    const double* a = I.Aw + (size_t)j * I.ldw;
+    const double* b = I.Bw + (size_t)j * I.ldw;
     double s = 0.0;
     for (int i = lane; i < m; i += 32) s += (a[i] + 0.1 * cs[i] * b[i]) * v[i];
     B2_UNROLL
@@ -245,8 +315,8 @@ __device__ __forceinline__ void dn_fill_vals(const DenseInst& I, const double* x
       while (rem >= nt - tb) { rem -= nt - tb; tb++; }
       const int a0 = (tb + rem) * 8, b0 = tb * 8;
       const int ra = a0 + g, cb = b0 + g;
-      const double* pa = I.Bt + (size_t)(ra < n ? ra : 0) * m;
-      const double* pb = I.Bt + (size_t)(cb < n ? cb : 0) * m;
+      const double* pa = I.Bw + (size_t)(ra < n ? ra : 0) * I.ldw;
+      const double* pb = I.Bw + (size_t)(cb < n ? cb : 0) * I.ldw;
       double c0 = 0.0, c1 = 0.0;
 #pragma unroll 4
       for (int k0 = 0; k0 < m; k0 += 4) {
@@ -268,8 +338,8 @@ __device__ __forceinline__ void dn_fill_vals(const DenseInst& I, const double* x
     o += nh;
   }
   for (int q = tid; q < n * m; q += NT) {   // S3
-    const int i = q % m;
-    vs[o + q] = I.At[q] + 0.1 * cs[i] * I.Bt[q];
+    const int j = q / m, i = q - j * m;
+    vs[o + q] = I.Aw[(size_t)j * I.ldw + i] + 0.1 * cs[i] * I.Bw[(size_t)j * I.ldw + i];
   }
   o += n * m;
   for (int q = tid; q < n * nc; q += NT) {  // S4
@@ -346,8 +416,17 @@ __global__ void __launch_bounds__(NT) k_nls_dense(BatchPlanDev P, DenseNlsModel 
   B2_DYN_SMEM(raw);
   __shared__ int cnt[4];
   __shared__ int s_inst;
+  __shared__ __align__(8) unsigned long long mbar;
   const int tid = threadIdx.x;
   const int n = M.n, m = M.m, nc = M.ncon, N = n + m + nc;
+#ifndef B2_EMULATE
+  if (tid == 0) mbar_init(&mbar, 1);
+#endif
+  // A and B of the instance live in the (dead) packed-triangle area while the model is evaluated
+  const int lds = (m % 2 == 0) ? m + 4 : m;             // padded: conflict-free tensor-core fragment loads
+  const bool can_stage = 2 * (long long)n * lds <= P.npacked;
+  uint32_t tma_phase = 0;
+  bool staged = false;
   double* st = reinterpret_cast<double*>(raw + ((batched_smem_bytes(N, P.npacked) + 15) & ~(size_t)15));
   double* x = st;            double* xt = x + n;       double* Jxtr = xt + n;   double* t1 = Jxtr + n;
   double* cr = t1 + n;       double* cq = cr + n;
@@ -385,6 +464,15 @@ __global__ void __launch_bounds__(NT) k_nls_dense(BatchPlanDev P, DenseNlsModel 
     I.Ct = M.Ct + (size_t)b * M.stride_C;
     I.y = M.y + (size_t)b * M.stride_y;
     I.e = M.e + (size_t)b * M.stride_e;
+    I.Aw = I.At; I.Bw = I.Bt; I.ldw = m;
+    staged = false;
+    auto ensure_staged = [&]() {
+      if (can_stage && !staged) {
+        double* Pk = reinterpret_cast<double*>(raw);
+        if (dn_stage_model<NT>(I, Pk, Pk + (size_t)n * lds, lds, &mbar, tma_phase)) tma_phase ^= 1;
+        staged = true;
+      }
+    };
     const double* x0 = M.x0 + (size_t)b * M.stride_x0;
     for (int j = tid; j < n; j += NT) x[j] = x0[j];
     for (int k = tid; k < nc; k += NT) lam[k] = M.y0 ? M.y0[(size_t)b * nc + k] : 0.0;
@@ -398,6 +486,7 @@ __global__ void __launch_bounds__(NT) k_nls_dense(BatchPlanDev P, DenseNlsModel 
     double fx = 0.0, normdual = 0.0, normprimal = 0.0, normdualhat = 0.0, normprimalhat = 0.0;
     bool first_system = true;
 
+    ensure_staged();
     dn_residual<NT>(I, x, Fx, snx, csx, scr);
     neval_res++;
     if (cta_nonfinite<NT>(Fx, m)) {
@@ -506,6 +595,8 @@ __global__ void __launch_bounds__(NT) k_nls_dense(BatchPlanDev P, DenseNlsModel 
               if (!(rho <= prm.rho_max)) break;
             }
             if (stage > 0 && rho <= prm.rho_max) rho_old = rho;
+            staged = false;                       // the triangle went over the staged model
+            I.Aw = I.At; I.Bw = I.Bt; I.ldw = m;
             nfact += nfacti;
             nlinsolve++;
             if (rho > prm.rho_max || !success || cta_nonfinite<NT>(d, N) || fx >= 1e60) {
@@ -514,6 +605,7 @@ __global__ void __launch_bounds__(NT) k_nls_dense(BatchPlanDev P, DenseNlsModel 
             }
             for (int k = tid; k < nc; k += NT) dlam[k] = -d[n + m + k];
             __syncthreads();
+            ensure_staged();
           }
           B2_T0(tq3);
           if (inner_iter == 0) {   // extrapolation step (:656-670)
