@@ -3,6 +3,7 @@
 // analysis for the shared pattern, then every verb is ONE kernel launch with one CTA per instance.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -186,13 +187,45 @@ int BatchEngine::init(int dev, int64_t nbatch) {
     phw_ptr.push_back((int32_t)phw_sn.size());
     phb_ptr.push_back((int32_t)phb_sn.size());
   }
+  // width-1 supernodes per level, flat (factorization leaves first)
+  std::vector<int32_t> lw_ptr(1, 0), lw_nleaf;
+  std::vector<int4> lw_meta;
+  std::vector<int2> lf_ent;
+  for (int l = 0; l < S.nlevels; l++) {
+    int nleaf = 0;
+    for (int pass = 0; pass < 2; pass++)
+      for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; q++) {
+        const int s = S.level_sn[q];
+        if (S.scol[s + 1] - S.scol[s] != 1) continue;
+        const bool leaf = ct_ptr[s + 1] == ct_ptr[s];
+        if (leaf != (pass == 0)) continue;
+        const int k = S.scol[s];
+        int4 mt;
+        mt.x = k; mt.y = (int)lf_ent.size(); mt.z = rb_ptr[s + 1] - rb_ptr[s]; mt.w = cbm[k];
+        lw_meta.push_back(mt);
+        for (int32_t p = rb_ptr[s]; p < rb_ptr[s + 1]; p++) {
+          int2 en;
+          en.x = cbm[k] + rb_idx[p]; en.y = k | (rb_idx[p] << 16);
+          lf_ent.push_back(en);
+        }
+        nleaf += leaf;
+      }
+    lw_nleaf.push_back(nleaf);
+    lw_ptr.push_back((int32_t)lw_meta.size());
+  }
+  {
+    int4 mt;
+    mt.x = 0; mt.y = (int)lf_ent.size(); mt.z = 0; mt.w = 0;
+    lw_meta.push_back(mt);   // sentinel: end of the entries
+  }
   plan.N = N; plan.nnz = (int)S.nnz; plan.nsuper = S.nsuper; plan.nphase = S.nlevels;
   plan.npacked = (int)npacked; plan.nvar = (int)S.nvar; plan.nequ = (int)S.nequ; plan.ncon = (int)S.ncon;
   plan.nmulti = (int)multi_dst.size();
   if (up(S.perm, &plan.perm) || up(cbm, &plan.cbm) || up(S.scol, &plan.sc0) || up(rb_ptr, &plan.rb_ptr) ||
       up(rb_idx, &plan.rb_idx) || up(ct_ptr, &plan.ct_ptr) || up(ct_col, &plan.ct_col) ||
       up(S.level_ptr, &plan.ph_ptr) || up(S.level_sn, &plan.ph_sn) || up(phw_ptr, &plan.phw_ptr) ||
-      up(phw_sn, &plan.phw_sn) || up(phb_ptr, &plan.phb_ptr) || up(phb_sn, &plan.phb_sn) || up(dst_single, &plan.dst_single) ||
+      up(phw_sn, &plan.phw_sn) || up(lw_ptr, &plan.lw_ptr) || up(lw_nleaf, &plan.lw_nleaf) || up(lw_meta, &plan.lw_meta) ||
+      up(lf_ent, &plan.lf_ent) || up(phb_ptr, &plan.phb_ptr) || up(phb_sn, &plan.phb_sn) || up(dst_single, &plan.dst_single) ||
       up(multi_dst, &plan.multi_dst) || up(multi_ptr, &plan.multi_ptr) || up(multi_coo, &plan.multi_coo))
     return -1;
   if (alloc(&d_vals, (size_t)batch * S.nnz) || alloc(&d_rhs, (size_t)batch * N) ||
@@ -336,9 +369,16 @@ int b2b_analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* col
   opt.ordering = ordering;
   opt.user_perm = user_perm;
   opt.build_spmv = false;
-  // the packed dense triangle stores structural zeros for free, so amalgamate generously:
-  // wide supernodes keep the tensor-core tiles full
-  opt.relax_always = 16; opt.relax_z1 = 0.6; opt.relax_z2 = 0.4; opt.relax_z3 = 0.25;
+  // the packed dense triangle stores structural zeros for free, but every column merged into the root
+  // supernode lengthens its sequential pivot chain: only short chains are amalgamated (measured on
+  // config 5: 129-column root 272 k cycles per instance, 65-column root + 143 leaves 197 k)
+  opt.relax_always = 8; opt.relax_w1 = 16; opt.relax_z1 = 0.3; opt.relax_w2 = 32; opt.relax_z2 = 0.15; opt.relax_z3 = 0.0;
+  if (const char* e = getenv("B2B_RELAX")) {   // developer knob: "always,w1,z1,w2,z2,z3"
+    int a, w1, w2; double z1, z2, z3;
+    if (sscanf(e, "%d,%d,%lf,%d,%lf,%lf", &a, &w1, &z1, &w2, &z2, &z3) == 6) {
+      opt.relax_always = a; opt.relax_w1 = w1; opt.relax_z1 = z1; opt.relax_w2 = w2; opt.relax_z2 = z2; opt.relax_z3 = z3;
+    }
+  }
   if (!b2::analyze(N, nnz, rows1, cols1, nvar, nequ, ncon, opt, h->eng.sym)) {
     snprintf(b2::g_last_error, sizeof(b2::g_last_error), "b2b_analyze: %s", h->eng.sym.error.c_str());
     delete h;

@@ -40,6 +40,12 @@ struct BatchPlanDev {
   const int32_t* phw_sn;
   const int32_t* phb_ptr;    // nphase+1: supernodes of width > 1: backward
   const int32_t* phb_sn;
+  // width-1 supernodes per level as FLAT lists (no per-supernode chain of dependent plan reads): the
+  // supernodes without contributing columns (leaves of the factorization) first
+  const int32_t* lw_ptr;     // nphase+1 into lw_meta
+  const int32_t* lw_nleaf;   // nphase: how many of the level's width-1 supernodes are factorization leaves
+  const int4* lw_meta;       // (column k, first entry, entries = rows below, cbm[k]); one sentinel at the end
+  const int2* lf_ent;        // per row below: (packed index of L(row, k), k | row << 16)
   const int32_t* dst_single; // nnz: packed destination of a COO entry that is alone in its slot, else -1
   const int32_t* multi_dst;  // nmulti
   const int32_t* multi_ptr;  // nmulti+1 into multi_coo
@@ -220,17 +226,22 @@ __device__ __forceinline__ void batched_instance(const BatchPlanDev& P, unsigned
     B2_TICK(31);
     // ---------------------------------------------------------------- factorize
     for (int ph = 0; ph < P.nphase; ph++) {
-      const int q0 = P.ph_ptr[ph], q1 = P.ph_ptr[ph + 1];
-      // width-1 supernodes without contributions (the leaves): one warp each, all in parallel
-      for (int qs = q0 + warp; qs < q1; qs += NW) {
-        const int s = P.ph_sn[qs];
-        const int c0 = P.sc0[s];
-        if (P.sc0[s + 1] - c0 != 1 || P.ct_ptr[s + 1] != P.ct_ptr[s]) continue;
-        const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
-        const int32_t* rb = P.rb_idx + P.rb_ptr[s];
-        const int base = cbm[c0];
-        const double rdk = rcp_nr(Pk[base + c0]);
-        for (int i = lane; i < nrb; i += 32) Pk[base + rb[i]] *= rdk;
+      // width-1 supernodes without contributions (the leaves): reciprocal pivots, then ONE flat pass over
+      // all their entries (a warp per leaf paid a chain of four dependent plan reads per leaf)
+      {
+        const int a0 = P.lw_ptr[ph], nl = P.lw_nleaf[ph];
+        if (nl > 0) {
+          for (int q = tid; q < nl; q += NT) {
+            const int4 mt = P.lw_meta[a0 + q];
+            lk[mt.x] = rcp_nr(Pk[mt.w + mt.x]);
+          }
+          const int e0 = P.lw_meta[a0].y, e1 = P.lw_meta[a0 + nl].y;
+          __syncthreads();
+          for (int e = e0 + tid; e < e1; e += NT) {
+            const int2 en = P.lf_ent[e];
+            Pk[en.x] *= lk[en.y & 0xffff];
+          }
+        }
       }
       __syncthreads();
       B2_TICK(32 + 2 * ph);
@@ -427,20 +438,26 @@ __device__ __forceinline__ void batched_instance(const BatchPlanDev& P, unsigned
   // backward: L' x = z, levels in reverse; the rows below a supernode belong to higher levels
   // and are already final
   for (int ph = P.nphase - 1; ph >= 0; ph--) {
-    const int q0 = P.ph_ptr[ph], q1 = P.ph_ptr[ph + 1];
-    // rows below: width-1 supernodes one warp each (lanes over the rows, shuffle reduction)
-    for (int qs = q0 + warp; qs < q1; qs += NW) {
-      const int s = P.ph_sn[qs];
-      const int c0 = P.sc0[s];
-      if (P.sc0[s + 1] - c0 != 1) continue;
-      const int nrb = P.rb_ptr[s + 1] - P.rb_ptr[s];
-      const int32_t* rb = P.rb_idx + P.rb_ptr[s];
-      const int base = cbm[c0];
-      double acc = 0.0;
-      for (int i = lane; i < nrb; i += 32) acc += Pk[base + rb[i]] * xs[rb[i]];
-      B2_UNROLL
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) xs[c0] -= acc;
+    // rows below: width-1 supernodes, eight lanes each (flat lists, fixed-order shuffle tree)
+    {
+      const int a0 = P.lw_ptr[ph], nw1 = P.lw_ptr[ph + 1] - a0;
+      for (int qb = 0; qb < nw1; qb += NT >> 3) {
+        const int q = qb + (tid >> 3);
+        double acc = 0.0;
+        int col = -1;
+        if (q < nw1) {
+          const int4 mt = P.lw_meta[a0 + q];
+          col = mt.x;
+          for (int i = tid & 7; i < mt.z; i += 8) {
+            const int2 en = P.lf_ent[mt.y + i];
+            acc += Pk[en.x] * xs[en.y >> 16];
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (col >= 0 && (tid & 7) == 0) xs[col] -= acc;
+      }
     }
     __syncthreads();
     B2_TICK(46 + (ph & 1));

@@ -32,6 +32,8 @@ using std::isnan;
 #define __align__(x)
 
 struct uint3 { unsigned x, y, z; };
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
 struct dim3 {
   unsigned x, y, z;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
