@@ -646,6 +646,25 @@ int Engine::build_plan() {
     dsptr[S.nsuper] = off;
     W.level = S.nlevels; W.branch = 9;
     if (W.count) fact_launches.push_back(W);
+    // explicit inverses of the diagonal blocks of the chained big-front solves (after the write-back:
+    // the launch-chain fronts get their factored diagonal blocks from the staging area)
+    {
+      std::vector<int32_t> linv_idx(S.nsuper, -1);
+      Launch V; V.kind = LK_LINV; V.off = (int64_t)items.size();
+      n_linv = 0;
+      for (int s = 0; s < S.nsuper; s++) {
+        const int nblk = (front_w(s) + SB - 1) / SB;
+        if (front_m(s) <= (int)solve_big_m || nblk < inv_min_blk || inv_min_blk <= 0) continue;
+        linv_idx[s] = (int32_t)n_linv;
+        for (int c = 0; c < nblk; c++) { items.push_back(s); items.push_back(c); V.count++; }
+        n_linv += nblk;
+      }
+      V.level = S.nlevels + 1; V.branch = 9;
+      if (V.count) fact_launches.push_back(V);
+      if (upload(&d_linv_idx, linv_idx, bytes_device)) return -1;
+      if (dalloc(&d_linv, (size_t)std::max<int64_t>(n_linv, 1) * SB * SB, bytes_device)) return -1;
+      plan.linv_idx = d_linv_idx; plan.Linv = d_linv;
+    }
     if (upload(&d_dsptr, dsptr, bytes_device)) return -1;
     if (dalloc(&d_dstage, (size_t)off, bytes_device)) return -1;
     plan.dstage = d_dstage; plan.dsptr = d_dsptr;
@@ -803,7 +822,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_fl_ptr, d_fl_ent, d_sf_ptr, d_sf_ent, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_linv_idx, d_linv, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_fl_ptr, d_fl_ent, d_sf_ptr, d_sf_ent, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_mismatch) cudaFreeHost(h_mismatch);
   if (cstream) cudaStreamDestroy(cstream);
@@ -839,6 +858,9 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       break;
     case LK_DIAG:
       B2_LAUNCH(k_diag, L.count, 256, DIAG_SMEM, st, plan, it, L.count, L.jb, L.flag);
+      break;
+    case LK_LINV:
+      B2_LAUNCH(k_linv, L.count, SB, 0, st, plan, it, L.count);
       break;
     case LK_DIAG_WRITEBACK:
       B2_LAUNCH(k_diag_writeback, L.count, 256, 0, st, plan, it, L.count);

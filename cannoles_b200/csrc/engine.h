@@ -24,6 +24,7 @@ enum LaunchKind : int {
   LK_BWD_TINY,
   LK_DIAG,
   LK_DAG,
+  LK_LINV,
 };
 
 struct Launch {
@@ -75,6 +76,10 @@ struct Engine {
   double small_max_m = 72;   // fronts up to this order take the shared-memory path (measured: 72 beats 128 and 40 on C4)
   int tiny_max_m = 8;        // fronts up to this order (4 / 8 classes) take the one-thread-per-front kernels
   int tiny_solve_max_m = 16; // ... and up to this order (16 / 32 classes) in the solves only (measured: 32 loses to a warp per front)
+  // fronts of the multi-CTA solves with at least this many pivot blocks get explicit inverses of their
+  // unit-lower 64 x 64 diagonal blocks (k_linv, at the end of the factorization): the in-block
+  // substitution by one warp (2.4 k cycles on the chain of every block) becomes a mat-vec by the CTA
+  int inv_min_blk = 2;
   double solve_big_m = 96;   // fronts above this order take the multi-CTA solve kernels (measured: 96 < 192 < 384)
 
   // device buffers
@@ -95,7 +100,9 @@ struct Engine {
           *d_amap_ptr = nullptr;
   double *d_Lx = nullptr, *d_CB = nullptr, *d_dvec = nullptr, *d_dstage = nullptr;
   int64_t *d_dsptr = nullptr, *d_asm_cptr = nullptr, *d_asm_off = nullptr, *d_sb_ptr = nullptr;
-  int32_t *d_asm_ent = nullptr, *d_asm_rc = nullptr, *d_sb_src = nullptr, *d_sb_flag = nullptr;
+  int32_t *d_asm_ent = nullptr, *d_asm_rc = nullptr, *d_sb_src = nullptr, *d_sb_flag = nullptr, *d_linv_idx = nullptr;
+  double* d_linv = nullptr;
+  int64_t n_linv = 0;
   uint8_t* d_ug_row = nullptr;
   int32_t *d_ug_ptr = nullptr, *d_ug_src = nullptr;   // per-row gather of the children's update vectors (k_fwd, k_fwd_tiny)
   int64_t nsflag = 0;          // pivot blocks of the big fronts (0: no multi-CTA solves)

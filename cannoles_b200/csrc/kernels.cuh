@@ -1589,6 +1589,56 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_bwd_tiny(PlanDev P, const int32
 }
 
 // ------------------------------------------------------------------------------------------
+// Explicit inverse of a unit-lower 64 x 64 diagonal block of a big front, item = (front, block),
+// one CTA of 64 threads, in place in shared memory: row i of X = L^{-1} is
+//   X(i, j) = -( L(i, j) + sum_{j < k < i} L(i, k) X(k, j) ),   j < i,
+// thread j owns column j, the rows go one after the other (row i of L is still intact when row i
+// of X is formed: it is copied to a row buffer first).  Rows beyond the block are identity rows.
+// Runs once per factorization, off every critical path; the solves read the inverse instead of L.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SB) k_linv(PlanDev P, const int32_t* __restrict__ items, int nitems) {
+  const int b = blockIdx.x;
+  if (b >= nitems) return;
+  const int s = items[2 * b], c = items[2 * b + 1];
+  const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
+  const int m = (int)(P.rptr[s + 1] - P.rptr[s]);
+  const int i0 = c * SB, nrow = min(SB, w - i0);
+  const double* Lp = P.Lx + P.lptr[s];
+  double* out = P.Linv + (size_t)(P.linv_idx[s] + c) * SB * SB;
+  __shared__ double X[SB * (SB + 1)];      // [row][col], ld SB + 1
+  __shared__ double rowL[2][SB];
+  const int tid = threadIdx.x;
+  for (int k = 0; k < SB; k++) {           // thread <-> row: coalesced over the rows of a column
+    const int i = tid;
+    double v = (i == k) ? 1.0 : 0.0;
+    if (i < nrow && k < i) v = Lp[(i0 + i) + (size_t)(i0 + k) * m];
+    X[i * (SB + 1) + k] = v;
+  }
+  __syncthreads();
+  const int j = tid;
+  for (int i = 1; i < nrow; i++) {
+    double* rl = rowL[i & 1];
+    rl[j] = X[i * (SB + 1) + j];
+    __syncthreads();
+    if (j < i) {
+      double a0 = rl[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = j + 1;
+      for (; k + 3 < i; k += 4) {
+        a0 += rl[k] * X[k * (SB + 1) + j];
+        a1 += rl[k + 1] * X[(k + 1) * (SB + 1) + j];
+        a2 += rl[k + 2] * X[(k + 2) * (SB + 1) + j];
+        a3 += rl[k + 3] * X[(k + 3) * (SB + 1) + j];
+      }
+      for (; k < i; k++) a0 += rl[k] * X[k * (SB + 1) + j];
+      X[i * (SB + 1) + j] = -((a0 + a1) + (a2 + a3));
+    }
+    // (the next row's buffer is the other one; rows < i + 1 of X are final after the next barrier)
+  }
+  __syncthreads();
+  for (int k = 0; k < SB; k++) out[tid + (size_t)k * SB] = X[tid * (SB + 1) + k];
+}
+
+// ------------------------------------------------------------------------------------------
 // (3b) big fronts: the triangular solves of ONE front are spread over many CTAs, one per
 // 64-row chunk (forward) / 64-column block (backward), chained by flags in global memory: a CTA
 // only ever waits for CTAs with a smaller blockIdx of the same launch (the items are ordered
@@ -1661,10 +1711,16 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
     t[tid] = acc;
   }
   __syncthreads();
-  if (pivot) {  // own diagonal block, strict lower part (prefetched before any wait)
-    for (int e = tid; e < SB * SB; e += 256) {
-      const int i = e % SB, j = e / SB;
-      Ld[i + j * (SB + 1)] = (i < nrow && j < i) ? Lp[(i0 + i) + (size_t)(i0 + j) * m] : 0.0;
+  const int li = P.linv_idx[s];              // >= 0: explicit inverses of the diagonal blocks (k_linv)
+  if (pivot) {  // own diagonal block (prefetched before any wait): its inverse, or the strict lower part
+    if (li >= 0) {
+      const double* Xi = P.Linv + (size_t)(li + c) * SB * SB;
+      for (int e = tid; e < SB * SB; e += 256) Ld[(e % SB) + (e / SB) * (SB + 1)] = Xi[e];
+    } else {
+      for (int e = tid; e < SB * SB; e += 256) {
+        const int i = e % SB, j = e / SB;
+        Ld[i + j * (SB + 1)] = (i < nrow && j < i) ? Lp[(i0 + i) + (size_t)(i0 + j) * m] : 0.0;
+      }
     }
   }
   __syncthreads();   // Ld (and t) complete before warp 0 uses them: chunk 0 has no wait in between
@@ -1694,7 +1750,22 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
     if (tid < SB) t[tid] -= (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
     __syncthreads();
   }
-  if (pivot) {
+  if (pivot && li >= 0) {
+    // y = L_cc^{-1} t as a mat-vec by the whole CTA: thread <-> (row r, quarter q of the columns)
+    double acc = 0.0, acc2 = 0.0;
+    B2_UNROLL
+    for (int k = 0; k < 16; k += 2) {
+      acc += Ld[r + (q * 16 + k) * (SB + 1)] * t[q * 16 + k];
+      acc2 += Ld[r + (q * 16 + k + 1) * (SB + 1)] * t[q * 16 + k + 1];
+    }
+    red[q][r] = acc + acc2;
+    __syncthreads();
+    if (tid < nrow) {
+      const double y = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+      publish_value(ypub + c0 + i0 + tid, y);
+      x[c0 + i0 + tid] = y / P.dvec[c0 + i0 + tid];
+    }
+  } else if (pivot) {
     // unit-lower substitution inside the block by warp 0, 8 columns at a time: every lane solves
     // the 8 x 8 triangle redundantly in registers (no communication on the chain), then updates
     // its two rows (lane, lane + 32) below it
@@ -1759,9 +1830,15 @@ __global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __res
   B2_TICK(54);
   if (tid < SB) sc[tid] = (tid < ncol) ? x[c0 + j0 + tid] : 0.0;
   for (int i = w + tid; i < m; i += 256) xb[i - w] = x[P.rowidx[r0 + i]];
-  for (int e = tid; e < SB * SB; e += 256) {   // own diagonal block: Ld[i][j] = L(j0+i, j0+j), j < i
-    const int i = e % SB, j = e / SB;
-    Ld[i + j * (SB + 1)] = (i < ncol && j < i) ? Lp[(j0 + i) + (size_t)(j0 + j) * m] : 0.0;
+  const int li = P.linv_idx[s];                // >= 0: explicit inverses of the diagonal blocks (k_linv)
+  if (li >= 0) {
+    const double* Xi = P.Linv + (size_t)(li + c) * SB * SB;
+    for (int e = tid; e < SB * SB; e += 256) Ld[(e % SB) + (e / SB) * (SB + 1)] = Xi[e];
+  } else {
+    for (int e = tid; e < SB * SB; e += 256) {   // own diagonal block: Ld[i][j] = L(j0+i, j0+j), j < i
+      const int i = e % SB, j = e / SB;
+      Ld[i + j * (SB + 1)] = (i < ncol && j < i) ? Lp[(j0 + i) + (size_t)(j0 + j) * m] : 0.0;
+    }
   }
   __syncthreads();
   B2_TICK(55);
@@ -1820,6 +1897,26 @@ __global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __res
   }
   __syncthreads();
   B2_TICK(57);
+  if (li >= 0) {
+    // x = L_cc^{-T} sc as a mat-vec by the whole CTA: thread <-> (column r, quarter q of the rows)
+    __shared__ double redb[4][SB];
+    const int r = tid & 63, q = tid >> 6;
+    double acc = 0.0, acc2 = 0.0;
+    B2_UNROLL
+    for (int k = 0; k < 16; k += 2) {
+      acc += Ld[(q * 16 + k) + r * (SB + 1)] * sc[q * 16 + k];
+      acc2 += Ld[(q * 16 + k + 1) + r * (SB + 1)] * sc[q * 16 + k + 1];
+    }
+    redb[q][r] = acc + acc2;
+    __syncthreads();
+    if (tid < ncol) {
+      const double xv = (redb[0][tid] + redb[1][tid]) + (redb[2][tid] + redb[3][tid]);
+      x[c0 + j0 + tid] = xv;
+      publish_value(xpub + c0 + j0 + tid, xv);
+    }
+    B2_TICK(58);
+    return;
+  }
   // L_cc^T x = sc inside the block by warp 0, 8 columns at a time from the end: every lane solves
   // the 8 x 8 triangle redundantly, then updates its two entries (lane, lane + 32) before it
   if (warp == 0) {

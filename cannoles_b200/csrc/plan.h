@@ -30,6 +30,8 @@ struct PlanDev {
   const int64_t* sb_ptr;   // big-front solve: per (chunk, row) CSR pointers into sb_src (SB + 1 per chunk)
   const int32_t* sb_src;   // offsets into the update-vector storage, in child order
   const int32_t* sb_flag;  // per front: offset of its block flags (big fronts only)
+  const int32_t* linv_idx; // per front: first slot in Linv of the explicit inverses of its unit-lower diagonal blocks, -1: none
+  double* Linv;            // SB x SB per slot, column-major, full lower triangle (unit diagonal), zeros above
   const int32_t* ug_ptr;   // forward solve of the other fronts: per front row (rptr[s] + i) the range in ug_src
   const int32_t* ug_src;   //   of the child update entries (offsets into upd) that land on it, in child order
   const uint8_t* ug_row;   //   and the row of the front each entry lands on (fronts of order <= 255: the thread-per-front kernels)

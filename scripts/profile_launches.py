@@ -13,7 +13,7 @@ from cannoles_b200 import _capi  # noqa: E402
 from cannoles_b200.linsolve import B200Struct  # noqa: E402
 from cannoles_b200.workloads import first_system, make_config  # noqa: E402
 
-KIND = ["front_small", "assemble_large", "diag_writeback", "trsm", "update", "fwd", "bwd", "fwd_big", "bwd_big", "front_tiny", "fwd_tiny", "bwd_tiny", "diag", "dag"]
+KIND = ["front_small", "assemble_large", "diag_writeback", "trsm", "update", "fwd", "bwd", "fwd_big", "bwd_big", "front_tiny", "fwd_tiny", "bwd_tiny", "diag", "dag", "linv"]
 EPS = 2.0 ** -52
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c4"
 size = int(sys.argv[2]) if len(sys.argv) > 2 else None
