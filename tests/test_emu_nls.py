@@ -83,3 +83,43 @@ def test_wrong_layout_is_rejected(emu_lib):
             S.solve(mod["At"], mod["Bt"], mod["Ct"], mod["y"], mod["e"], mod["x0"])
     finally:
         S.close()
+
+
+def test_partitioned_batch_gloo_world2(tmp_path, emu_lib):
+    """SURVEY 8(e) for the batched loop: two ranks (gloo, CPU emulator) each solve their contiguous block
+    of the instances, one all_gather of the records at the end == the records of a single-rank run."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import torch.distributed as dist\n"
+        "from cannoles_b200 import _capi\n"
+        "from cannoles_b200.batched import partition, gather_records\n"
+        "from cannoles_b200.batched_nls import B200BatchNLS, pack_dense_models\n"
+        f"lib = _capi.bind_library({os.path.join(root, 'tests', 'hostsim', 'libb2_emu.so')!r})\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "total, dims = 5, (10, 16, 3)\n"
+        "def run(lo, hi):\n"
+        "    mod = pack_dense_models(range(lo, hi), *dims)\n"
+        "    S = B200BatchNLS(hi - lo, *dims, _lib=lib)\n"
+        "    rec = S.solve(mod['At'], mod['Bt'], mod['Ct'], mod['y'], mod['e'], mod['x0'])\n"
+        "    S.close()\n"
+        "    return rec\n"
+        "lo, hi = partition(total, r, w)\n"
+        "allrec = gather_records(run(lo, hi), dist)\n"
+        "assert allrec.shape[0] == total\n"
+        "assert np.array_equal(allrec, run(0, total))\n"
+        "assert (allrec[:, 0] == 1).all()\n"
+        "dist.barrier(); dist.destroy_process_group()\n"
+        "print('ok', r)\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
