@@ -20,6 +20,6 @@ t = list(out)
 print("assemble", t[31]-t[30])
 print("ph0 (a)", t[32]-t[31], "(b)", t[33]-t[32])
 print("ph1 (a)", t[34]-t[33], "(b)", t[35]-t[34])
-print("root: (a) update", t[50], " panel load", t[51], " ldlt+subst", t[52], " trailing", t[53])
+print("root: (a) update", t[50], " dense LDL^T (cta_ldlt_packed)", t[51])
 print("inertia", t[41]-t[40], "solve", t[42]-t[41], "total", t[42]-t[30])
 print("solve split: load rhs + forward", t[43]-t[41], " diagonal", t[44]-t[43], " backward", t[45]-t[44], " (of which after the leaves pass of level 1:", t[45]-t[47], ", of level 0:", t[45]-t[46], ") store", t[42]-t[45])
