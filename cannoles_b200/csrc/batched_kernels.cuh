@@ -97,7 +97,7 @@ __device__ __forceinline__ void panel_update(double* Pk, const int32_t* cbm, con
         const int tr = jbeg + (ti0 + a) * 8 + g;        // A-fragment row (local)
         ra[a] = (ti0 + a < nti && tr < m) ? rowmap[tr] : -1;
       }
-#pragma unroll 2
+#pragma unroll 4
       for (int q0 = 0; q0 < K; q0 += 4) {
         const int q = q0 + t4;
         double bv = 0.0, av[STRIP];
@@ -355,6 +355,7 @@ __device__ __forceinline__ void batched_instance(const BatchPlanDev& P, unsigned
     // ---------------------------------------------------------------- assemble
     for (int i = tid; i < P.npacked; i += NT) Pk[i] = 0.0;
     __syncthreads();
+    B2_TICK(20);
     const int t_rho = P.nnz - P.nvar, t_del = t_rho - P.ncon;
     const bool over = has_rho || has_del;
     constexpr int U = 8;   // loads of U entries in flight per thread (16: no faster, measured)
@@ -379,19 +380,50 @@ __device__ __forceinline__ void batched_instance(const BatchPlanDev& P, unsigned
         Pk[dst[u]] = 0.0 + x;
       }
     }
-    for (int q = tid; q < P.nmulti; q += NT) {
-      const int p0 = P.multi_ptr[q], p1 = P.multi_ptr[q + 1];
-      double acc = 0.0;
-      for (int p = p0; p < p1; p++) {
-        const int t = P.multi_coo[p];
+    B2_TICK(21);
+    // slots with several COO contributors (every entry of the (1,1) block has two or three: residual
+    // Hessian, constraint Hessian, rho): summed in COO order from +0.0 like set_vals!, but the loads of
+    // SU slots x 3 contributors are issued together -- three dependent rounds of loads per pass instead
+    // of three per slot (17 k -> 6 k cycles on config 5)
+    {
+      constexpr int SU = 4, MC = 3;
+      auto value_of = [&](int t) -> double {
         double x = v[t];
         if (over) {
           if (has_rho && t >= t_rho) x = rho_b;
           else if (has_del && t >= t_del && t < t_rho) x = mdel_b;
         }
-        acc += x;
+        return x;
+      };
+      for (int q0 = tid; q0 < P.nmulti; q0 += NT * SU) {
+        int p0[SU], p1[SU], tt[SU][MC];
+        double xv[SU][MC];
+        B2_UNROLL
+        for (int u = 0; u < SU; u++) {
+          const int q = q0 + u * NT;
+          p0[u] = q < P.nmulti ? P.multi_ptr[q] : 0;
+          p1[u] = q < P.nmulti ? P.multi_ptr[q + 1] : 0;
+        }
+        B2_UNROLL
+        for (int u = 0; u < SU; u++)
+          B2_UNROLL
+          for (int k = 0; k < MC; k++) tt[u][k] = p0[u] + k < p1[u] ? P.multi_coo[p0[u] + k] : -1;
+        B2_UNROLL
+        for (int u = 0; u < SU; u++)
+          B2_UNROLL
+          for (int k = 0; k < MC; k++) xv[u][k] = tt[u][k] >= 0 ? value_of(tt[u][k]) : 0.0;
+        B2_UNROLL
+        for (int u = 0; u < SU; u++) {
+          const int q = q0 + u * NT;
+          if (q >= P.nmulti) continue;
+          double acc = 0.0;
+          B2_UNROLL
+          for (int k = 0; k < MC; k++)
+            if (tt[u][k] >= 0) acc += xv[u][k];
+          for (int p = p0[u] + MC; p < p1[u]; p++) acc += value_of(P.multi_coo[p]);
+          Pk[P.multi_dst[q]] = acc;
+        }
       }
-      Pk[P.multi_dst[q]] = acc;
     }
     __syncthreads();
     B2_TICK(31);
@@ -514,21 +546,29 @@ __device__ __forceinline__ void batched_instance(const BatchPlanDev& P, unsigned
       __syncthreads();
       for (int kb = 0; kb + 1 < w; kb += 8) {            // unit-lower pivot block, 8 columns at a time
         const int pw = min(8, w - kb);
+        // everything that does not depend on the solved values first, in registers: column bases, the
+        // 8 x 8 triangle, this thread's row of the panel
+        int cb8[8];
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) cb8[c] = c < pw ? cbm[c0 + kb + c] : 0;
+        double l8[8][8], lrow[8];
+        B2_UNROLL
+        for (int c = 1; c < 8; c++)
+          B2_UNROLL
+          for (int t = 0; t < c; t++) l8[c][t] = c < pw ? Pk[cb8[t] + c0 + kb + c] : 0.0;
+        const int tr = kb + 8 + tid;
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) lrow[c] = (tr < w && c < pw) ? Pk[cb8[c] + c0 + tr] : 0.0;
         double y[8];
         B2_UNROLL
         for (int c = 0; c < 8; c++) y[c] = c < pw ? xs[c0 + kb + c] : 0.0;
         B2_UNROLL
         for (int c = 1; c < 8; c++)
           B2_UNROLL
-          for (int t = 0; t < c; t++)
-            if (c < pw) y[c] -= Pk[cbm[c0 + kb + t] + c0 + kb + c] * y[t];
-        const int tr = kb + 8 + tid;
+          for (int t = 0; t < c; t++) y[c] -= l8[c][t] * y[t];
         double acc = 0.0;
-        if (tr < w) {
-          B2_UNROLL
-          for (int c = 0; c < 8; c++)
-            if (c < pw) acc += Pk[cbm[c0 + kb + c] + c0 + tr] * y[c];
-        }
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) acc += lrow[c] * y[c];
         __syncthreads();                                 // everybody has read xs[c0 + kb ..]
         if (tr < w) xs[c0 + tr] -= acc;
         if (tid == 0) {
@@ -589,21 +629,30 @@ __device__ __forceinline__ void batched_instance(const BatchPlanDev& P, unsigned
       __syncthreads();
       for (int kb = ((w - 1) >> 3) << 3; kb >= 0; kb -= 8) {   // L11' x = z, 8 columns at a time from the end
         const int pw = min(8, w - kb);
+        // operands that do not depend on the solved values first, in registers
+        int cb8[8];
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) cb8[c] = c < pw ? cbm[c0 + kb + c] : 0;
+        double l8[8][8], lcol[8];
+        B2_UNROLL
+        for (int c = 6; c >= 0; c--)
+          B2_UNROLL
+          for (int t = c + 1; t < 8; t++) l8[c][t] = t < pw ? Pk[cb8[c] + c0 + kb + t] : 0.0;
+        {
+          const int base = tid < kb ? cbm[c0 + tid] + c0 + kb : 0;
+          B2_UNROLL
+          for (int c = 0; c < 8; c++) lcol[c] = (tid < kb && c < pw) ? Pk[base + c] : 0.0;   // L(kb + c, tid)
+        }
         double x8[8];
         B2_UNROLL
         for (int c = 0; c < 8; c++) x8[c] = c < pw ? xs[c0 + kb + c] : 0.0;
         B2_UNROLL
         for (int c = 6; c >= 0; c--)
           B2_UNROLL
-          for (int t = c + 1; t < 8; t++)
-            if (t < pw) x8[c] -= Pk[cbm[c0 + kb + c] + c0 + kb + t] * x8[t];
-        double acc = 0.0;
-        if (tid < kb) {                                   // earlier entries j < kb: z_j -= sum_c L(kb+c, j) x_c
-          const int base = cbm[c0 + tid] + c0 + kb;
-          B2_UNROLL
-          for (int c = 0; c < 8; c++)
-            if (c < pw) acc += Pk[base + c] * x8[c];
-        }
+          for (int t = c + 1; t < 8; t++) x8[c] -= l8[c][t] * x8[t];
+        double acc = 0.0;                                 // earlier entries j < kb: z_j -= sum_c L(kb+c, j) x_c
+        B2_UNROLL
+        for (int c = 0; c < 8; c++) acc += lcol[c] * x8[c];
         __syncthreads();
         if (tid < kb) xs[c0 + tid] -= acc;
         if (tid == 0) {

@@ -17,7 +17,7 @@ out = (C.c_longlong * 64)()
 lib.b2b_debug_clocks.argtypes = [C.POINTER(C.c_longlong)]
 lib.b2b_debug_clocks(out)
 t = list(out)
-print("assemble", t[31]-t[30])
+print("assemble", t[31]-t[30], " (zero", t[20]-t[30], " single-slot entries", t[21]-t[20], " multi-slot entries", t[31]-t[21], ")")
 print("ph0 (a)", t[32]-t[31], "(b)", t[33]-t[32])
 print("ph1 (a)", t[34]-t[33], "(b)", t[35]-t[34])
 print("root: (a) update", t[50], " dense LDL^T (cta_ldlt_packed)", t[51])
