@@ -259,17 +259,18 @@ def measure_system(lib, args, workload, size, ordering_name, steps, warmup, loca
         s.vals[nnz - nls.nvar:] = rho_used
         ok = step_host()
     rho_reason = "inertia correction (rho = 0 fails the inertia test under this ordering)" if rho_used > 0 else None
-    if ok and B.last_inertia == expected and rho_used == 0.0 and not (B.last_relres <= 1e-10):
+    if ok and B.last_inertia == expected and rho_used == 0.0 and not (B.last_relres <= 1e-12):
         # A Gauss-Newton KKT matrix (zero (1,1) block) can pass the inertia test at rho = 0 under a
         # nested-dissection order that happens to eliminate every r-vertex before its x-neighbours and
-        # still be numerically singular (C3: relres 5e-3 after refinement).  The reference's AMD path
+        # still be numerically singular (C3: relres between 5e-3 and 3e-12 after refinement, depending on rounding --
+        # above the 1e-12 acceptance bar either way).  The reference's AMD path
         # breaks down on that matrix and factors the rho0 system (tests/test_gpu_parity.py
         # ::test_c3_full_size_properties); time THAT system and say so.
         rho_used = EPS ** (1.0 / 3.0)
         s.vals[nnz - nls.nvar:] = rho_used
         ok = step_host()
         rho_reason = ("rho = 0 passes the inertia test under this ordering but the matrix is numerically singular "
-                      "(relres > 1e-10 after refinement); the rho0 system the reference's AMD path factors is timed")
+                      "(relres > 1e-12 after refinement); the rho0 system the reference's AMD path factors is timed")
     inertia = B.last_inertia
     if not ok or inertia != expected:
         raise RuntimeError(f"wrong inertia {inertia}, expected {expected}")
