@@ -860,7 +860,7 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       B2_LAUNCH(k_diag, L.count, 256, DIAG_SMEM, st, plan, it, L.count, L.jb, L.flag);
       break;
     case LK_LINV:
-      B2_LAUNCH(k_linv, L.count, SB, 0, st, plan, it, L.count);
+      B2_LAUNCH(k_linv, L.count, 256, 0, st, plan, it, L.count);
       break;
     case LK_DIAG_WRITEBACK:
       B2_LAUNCH(k_diag_writeback, L.count, 256, 0, st, plan, it, L.count);

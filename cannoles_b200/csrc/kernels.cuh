@@ -1589,14 +1589,16 @@ __global__ void __launch_bounds__(tiny_nt(MM)) k_bwd_tiny(PlanDev P, const int32
 }
 
 // ------------------------------------------------------------------------------------------
-// Explicit inverse of a unit-lower 64 x 64 diagonal block of a big front, item = (front, block),
-// one CTA of 64 threads, in place in shared memory: row i of X = L^{-1} is
-//   X(i, j) = -( L(i, j) + sum_{j < k < i} L(i, k) X(k, j) ),   j < i,
-// thread j owns column j, the rows go one after the other (row i of L is still intact when row i
-// of X is formed: it is copied to a row buffer first).  Rows beyond the block are identity rows.
-// Runs once per factorization, off every critical path; the solves read the inverse instead of L.
+// Explicit inverse X = L^{-1} of a unit-lower 64 x 64 diagonal block of a big front, item =
+// (front, block), one CTA of 256 threads, blocked in 8 x 8 sub-blocks:
+//   X_ii = L_ii^{-1}                                  (64 threads: one column of one block each)
+//   X_ij = -X_ii sum_{j <= k < i} L_ik X_kj,  j < i   block row after block row (7 steps); inside a
+//          step every thread forms ONE entry of T = L_i,: X_:,j (<= 56 terms), then of -X_ii T
+// Rows beyond the block are identity rows.  Runs once per factorization; the solves read X instead
+// of L (a 63-step row-by-row version with one thread per column took 63 us per launch: every step a
+// barrier and a dependent chain).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SB) k_linv(PlanDev P, const int32_t* __restrict__ items, int nitems) {
+__global__ void __launch_bounds__(256) k_linv(PlanDev P, const int32_t* __restrict__ items, int nitems) {
   const int b = blockIdx.x;
   if (b >= nitems) return;
   const int s = items[2 * b], c = items[2 * b + 1];
@@ -1605,37 +1607,68 @@ __global__ void __launch_bounds__(SB) k_linv(PlanDev P, const int32_t* __restric
   const int i0 = c * SB, nrow = min(SB, w - i0);
   const double* Lp = P.Lx + P.lptr[s];
   double* out = P.Linv + (size_t)(P.linv_idx[s] + c) * SB * SB;
-  __shared__ double X[SB * (SB + 1)];      // [row][col], ld SB + 1
-  __shared__ double rowL[2][SB];
+  constexpr int LD = SB + 1;
+  __shared__ double X[SB * LD];      // [row][col]: L on entry (unit lower, identity rows beyond nrow), X = L^{-1} in place
+  __shared__ double T[8 * LD];       // [row of the block row][col]
   const int tid = threadIdx.x;
-  for (int k = 0; k < SB; k++) {           // thread <-> row: coalesced over the rows of a column
-    const int i = tid;
+  for (int e = tid; e < SB * SB; e += 256) {
+    const int i = e % SB, k = e / SB;          // coalesced over the rows of a column
     double v = (i == k) ? 1.0 : 0.0;
     if (i < nrow && k < i) v = Lp[(i0 + i) + (size_t)(i0 + k) * m];
-    X[i * (SB + 1) + k] = v;
+    X[i * LD + k] = v;
   }
   __syncthreads();
-  const int j = tid;
-  for (int i = 1; i < nrow; i++) {
-    double* rl = rowL[i & 1];
-    rl[j] = X[i * (SB + 1) + j];
-    __syncthreads();
-    if (j < i) {
-      double a0 = rl[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int k = j + 1;
-      for (; k + 3 < i; k += 4) {
-        a0 += rl[k] * X[k * (SB + 1) + j];
-        a1 += rl[k + 1] * X[(k + 1) * (SB + 1) + j];
-        a2 += rl[k + 2] * X[(k + 2) * (SB + 1) + j];
-        a3 += rl[k + 3] * X[(k + 3) * (SB + 1) + j];
-      }
-      for (; k < i; k++) a0 += rl[k] * X[k * (SB + 1) + j];
-      X[i * (SB + 1) + j] = -((a0 + a1) + (a2 + a3));
+  {                                            // diagonal blocks: column jc of the inverse of block kb
+    const int kb = (tid & 63) >> 3, jc = tid & 7, o = kb * 8;
+    double x[8], l[8][8];
+    B2_UNROLL
+    for (int i = 1; i < 8; i++)
+      B2_UNROLL
+      for (int t = 0; t < i; t++) l[i][t] = X[(o + i) * LD + o + t];
+    B2_UNROLL
+    for (int i = 0; i < 8; i++) x[i] = (i == jc) ? 1.0 : 0.0;
+    B2_UNROLL
+    for (int i = 1; i < 8; i++) {
+      double sum = 0.0;
+      B2_UNROLL
+      for (int t = 0; t < i; t++) sum += l[i][t] * x[t];
+      if (i > jc) x[i] = -sum;
     }
-    // (the next row's buffer is the other one; rows < i + 1 of X are final after the next barrier)
+    __syncthreads();                           // every block has been read before anyone overwrites it
+    if (tid < SB) {
+      B2_UNROLL
+      for (int i = 0; i < 8; i++) X[(o + i) * LD + o + jc] = x[i];
+    }
   }
   __syncthreads();
-  for (int k = 0; k < SB; k++) out[tid + (size_t)k * SB] = X[tid * (SB + 1) + k];
+  for (int ib = 1; ib < 8; ib++) {             // block row ib: columns 0 .. 8 ib - 1 (still L there; X above and on the diagonal)
+    const int ncol = 8 * ib;
+    for (int e = tid; e < 8 * ncol; e += 256) {
+      const int r = e / ncol, cc = e - r * ncol;     // a warp: consecutive columns of one row
+      const double* lrow = X + (8 * ib + r) * LD;
+      double a0 = 0.0, a1 = 0.0;
+      int k = cc & ~7;                         // X_kj = 0 above the diagonal block of column cc
+      for (; k + 1 < ncol; k += 2) {
+        a0 += lrow[k] * X[k * LD + cc];
+        a1 += lrow[k + 1] * X[(k + 1) * LD + cc];
+      }
+      T[r * LD + cc] = a0 + a1;
+    }
+    __syncthreads();
+    for (int e = tid; e < 8 * ncol; e += 256) {
+      const int r = e / ncol, cc = e - r * ncol;
+      const double* xr = X + (8 * ib + r) * LD + 8 * ib;   // row r of X_ii
+      double a = 0.0;
+      B2_UNROLL
+      for (int t = 0; t < 8; t++) a += xr[t] * T[t * LD + cc];
+      X[(8 * ib + r) * LD + cc] = -a;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < SB * SB; e += 256) {
+    const int i = e % SB, k = e / SB;
+    out[e] = X[i * LD + k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
