@@ -30,5 +30,7 @@
   } while (0)
 
 namespace b2 {
-extern char g_last_error[512];
+// one message buffer per host thread: handles driven from different threads (one rank per thread)
+// never read each other's errors
+extern thread_local char g_last_error[512];
 }

@@ -10,7 +10,7 @@
 
 namespace b2 {
 
-char g_last_error[512] = "";
+thread_local char g_last_error[512] = "";
 
 namespace {
 
@@ -1060,13 +1060,15 @@ int Engine::assemble_and_factor(double eig_tol, int64_t* npos, int64_t* nzero, i
 #ifndef B2_EMULATE
   if (use_graph) {
     if (!g_fact) {
-      cudaGraph_t g;
+      cudaGraph_t g = nullptr;
       B2_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
       int rc = run_factor_launches();
       cudaError_t ce = cudaStreamEndCapture(stream, &g);
-      if (rc || ce != cudaSuccess) {
-        snprintf(g_last_error, sizeof(g_last_error), "graph capture of the factorization failed: %s",
-                 cudaGetErrorString(ce));
+      if (rc || ce != cudaSuccess) {   // (the capture has been ended either way: the stream stays usable)
+        if (!rc)    // a failed launch inside the capture has already left its own message
+          snprintf(g_last_error, sizeof(g_last_error), "graph capture of the factorization failed: %s",
+                   cudaGetErrorString(ce));
+        if (ce == cudaSuccess && g) cudaGraphDestroy(g);
         return -1;
       }
       B2_CUDA_OK(cudaGraphInstantiate(&g_fact, g, 0));
@@ -1193,12 +1195,14 @@ int Engine::solve_core(const double* d_b, double* d_o, int negate, int refine_st
 #ifndef B2_EMULATE
     if (use_graph) {
       if (!g_fwdbwd) {
-        cudaGraph_t g;
+        cudaGraph_t g = nullptr;
         B2_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         int rc = run_solve_launches();
         cudaError_t ce = cudaStreamEndCapture(stream, &g);
         if (rc || ce != cudaSuccess) {
-          snprintf(g_last_error, sizeof(g_last_error), "graph capture of the solve failed: %s", cudaGetErrorString(ce));
+          if (!rc)
+            snprintf(g_last_error, sizeof(g_last_error), "graph capture of the solve failed: %s", cudaGetErrorString(ce));
+          if (ce == cudaSuccess && g) cudaGraphDestroy(g);
           return -1;
         }
         B2_CUDA_OK(cudaGraphInstantiate(&g_fwdbwd, g, 0));

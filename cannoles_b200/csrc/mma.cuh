@@ -1,6 +1,10 @@
 // mma.cuh -- FP64 tensor-core fragment op shared by the single-system and the batched kernels.
 #pragma once
 #include "b2_cuda.h"
+#ifdef B2_EMULATE
+#include <cmath>
+#include <limits>
+#endif
 
 namespace b2 {
 
@@ -45,7 +49,12 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 // exact-rounding fix-up and a slow-path branch; the reciprocal of a pivot sits on the critical
 // path of every elimination step, where a DFMA costs ~39 cycles of latency.
 __device__ __forceinline__ double rcp_nr(double d) {
+// Edge: the seed flushes subnormal inputs to zero (ftz), so a zero OR subnormal pivot gives
+// x = +-inf, e = NaN / -inf and a NaN result, where the reference's division gives +-inf or a huge
+// finite number.  Either way the instance fails the inertia test (NaN compares false everywhere,
+// src/solver_types.jl:93-96; an exact zero also raises the breakdown flag) and the rho retry is taken.
 #ifdef B2_EMULATE
+  if (std::fabs(d) < 2.2250738585072014e-308) return std::numeric_limits<double>::quiet_NaN();   // as the hardware sequence
   return 1.0 / d;
 #else
   double x;
