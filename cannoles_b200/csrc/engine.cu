@@ -53,6 +53,7 @@ int Engine::build_plan() {
   std::vector<int32_t> sb_src, sb_flag(S.nsuper, 0);   // big-front solve: CSR gather of the child updates, flag offsets
   int64_t n_gather_chunks = 0;
   nsflag = 0;
+  n_stk = 0;
   fact_launches.clear(); fwd_launches.clear(); bwd_launches.clear();
   n_small = n_large = 0;
   std::vector<char> front_dag(S.nsuper, 0);
@@ -157,7 +158,7 @@ int Engine::build_plan() {
       }
     }
     if (!big.empty()) {   // multi-CTA solves: flag-chained chunks, items ordered so that waits look back
-      Launch F; F.kind = LK_FWD_BIG; F.off = (int64_t)items.size();
+      Launch F; F.kind = LK_FWD_BIG; F.off = (int64_t)items.size(); F.jb = n_stk++;
       int rmax = 0;
       for (int s : big) {
         int w = front_w(s), m = front_m(s);
@@ -193,7 +194,7 @@ int Engine::build_plan() {
         }
       }
       fwd_launches.push_back(F);
-      Launch Bk; Bk.kind = LK_BWD_BIG; Bk.off = (int64_t)items.size();
+      Launch Bk; Bk.kind = LK_BWD_BIG; Bk.off = (int64_t)items.size(); Bk.jb = n_stk++;
       Bk.smem = (int)((size_t)std::max(rmax, 1) * sizeof(double));
       for (int s : big) {
         int nblk = (front_w(s) + SB - 1) / SB;
@@ -724,6 +725,7 @@ int Engine::build_plan() {
   if (upload(&d_sb_src, sb_src, bytes_device)) return -1;
   if (upload(&d_sb_flag, sb_flag, bytes_device)) return -1;
   if (dalloc(&d_ypub, (size_t)(2 * S.N), bytes_device)) return -1;   // forward | backward publication slots
+  if (dalloc(&d_stk, (size_t)std::max(n_stk, 1), bytes_device)) return -1;
   plan.sb_ptr = d_sb_ptr; plan.sb_src = d_sb_src; plan.sb_flag = d_sb_flag;
   if (dalloc(&d_tflag, (size_t)(ntflag + 1 + ndcnt), bytes_device)) return -1;   // tile flags | ticket counter | counters
   plan.dcnt = d_tflag + ntflag + 1;
@@ -822,7 +824,7 @@ void Engine::destroy() {
   void* ptrs[] = {d_slot_ptr, d_coo_sorted, d_vals, d_nzval, d_rho_slot, d_delta_slot, d_rho_base,
                   d_delta_base, d_scol, d_rowidx, d_rel, d_child_ptr, d_child_idx, d_amap_slot,
                   d_amap_pos, d_perm, d_rptr, d_lptr, d_cbptr, d_uptr, d_amap_ptr, d_Lx, d_CB, d_dvec,
-                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_linv_idx, d_linv, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_fl_ptr, d_fl_ent, d_sf_ptr, d_sf_ent, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
+                  d_counts, d_items, d_dstage, d_dsptr, d_asm_cptr, d_asm_ent, d_asm_rc, d_asm_off, d_sb_ptr, d_sb_src, d_sb_flag, d_linv_idx, d_linv, d_ug_ptr, d_ug_src, d_ug_row, d_ypub, d_stk, d_tflag, d_dfr, d_tl_ptr, d_tl_ent, d_fl_ptr, d_fl_ent, d_sf_ptr, d_sf_ent, d_vals2, d_mismatch, d_x, d_upd, d_rhs, d_sol, d_res, d_out, d_part, d_Sp, d_Sj, d_Sslot};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h_mismatch) cudaFreeHost(h_mismatch);
   if (cstream) cudaStreamDestroy(cstream);
@@ -908,10 +910,10 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       else B2_LAUNCH(k_bwd_tiny<32>, (L.count + tiny_nt(32) - 1) / tiny_nt(32), tiny_nt(32), 0, st, plan, it, L.count, d_x);
       break;
     case LK_FWD_BIG:
-      B2_LAUNCH(k_fwd_big, L.count, 256, 0, st, plan, it, L.count, d_x, d_upd, d_ypub);
+      B2_LAUNCH(k_fwd_big, L.count, 256, 0, st, plan, it, L.count, d_x, d_upd, d_ypub, d_stk + L.jb);
       break;
     case LK_BWD_BIG:
-      B2_LAUNCH(k_bwd_big, L.count, 256, L.smem, st, plan, it, L.count, d_x, d_ypub + sym.N);
+      B2_LAUNCH(k_bwd_big, L.count, 256, L.smem, st, plan, it, L.count, d_x, d_ypub + sym.N, d_stk + L.jb);
       break;
     default: break;
   }
@@ -987,6 +989,7 @@ int Engine::run_factor_launches() {
 int Engine::run_solve_launches() {
   // publication slots of the multi-CTA solves: all-ones = "not yet published" (poll_value)
   if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
+  if (n_stk > 0) B2_CUDA_OK(cudaMemsetAsync(d_stk, 0, (size_t)n_stk * sizeof(int), stream));
   // measured: on systems with big fronts (C4) forking the solve levels costs more than it gains
   // (3.14 -> 3.49 ms), on systems made of small fronts only (C2) it gains 25 %
   const bool fork = solve_fork < 0 ? nsflag == 0 : solve_fork != 0;
@@ -1018,7 +1021,10 @@ int Engine::profile(int which, int max, int* kinds, int* cls, int* counts, doubl
     if (which == 0) {
       B2_CUDA_OK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
       if (ndag > 0) B2_CUDA_OK(cudaMemsetAsync(d_tflag, 0, (size_t)(ntflag + 1 + ndcnt) * sizeof(int), stream));
-    } else if (nsflag > 0) B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
+    } else if (nsflag > 0) {
+      B2_CUDA_OK(cudaMemsetAsync(d_ypub, 0xFF, (size_t)(2 * sym.N) * sizeof(double), stream));
+      B2_CUDA_OK(cudaMemsetAsync(d_stk, 0, (size_t)std::max(n_stk, 1) * sizeof(int), stream));
+    }
     B2_CUDA_OK(cudaEventRecord(evs[0], stream));
     for (size_t i = 0; i < LL.size(); i++) {
       launch_one(*LL[i], stream);

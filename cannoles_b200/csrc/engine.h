@@ -107,6 +107,8 @@ struct Engine {
   int32_t *d_ug_ptr = nullptr, *d_ug_src = nullptr;   // per-row gather of the children's update vectors (k_fwd, k_fwd_tiny)
   int64_t nsflag = 0;          // pivot blocks of the big fronts (0: no multi-CTA solves)
   double* d_ypub = nullptr;    // 2 N publication slots (forward y | backward x) of the multi-CTA solves
+  int* d_stk = nullptr;        // one ticket counter per multi-CTA solve launch (Launch::jb): virtual block indices
+  int n_stk = 0;
   int* d_flags = nullptr;
   unsigned long long* d_counts = nullptr;
   int32_t* d_items = nullptr;

@@ -1674,8 +1674,10 @@ __global__ void __launch_bounds__(256) k_linv(PlanDev P, const int32_t* __restri
 // ------------------------------------------------------------------------------------------
 // (3b) big fronts: the triangular solves of ONE front are spread over many CTAs, one per
 // 64-row chunk (forward) / 64-column block (backward), chained by flags in global memory: a CTA
-// only ever waits for CTAs with a smaller blockIdx of the same launch (the items are ordered
-// that way), so the waits cannot deadlock.  The strip of the panel a CTA needs next is
+// only ever waits for CTAs with a smaller VIRTUAL block index of the same launch (the items are
+// ordered that way; the virtual index is a ticket taken from an atomic counter when the CTA starts,
+// so it is the order in which the CTAs really became resident, whatever the hardware's dispatch
+// order): the waits cannot deadlock.  The strip of the panel a CTA needs next is
 // prefetched into registers BEFORE it waits, so the chain per block is: flag round trip +
 // 64 x 64 mat-vec + in-block substitution by one warp.
 // ------------------------------------------------------------------------------------------
@@ -1693,7 +1695,7 @@ __device__ __forceinline__ double poll_value(const double* p) {
 #else
   const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(p);
   unsigned long long u = *q;
-  while (u == ~0ull) u = *q;
+  while (u == ~0ull) u = *q;          // (a __nanosleep back-off was measured: +1 % on the C4 solve, the hand-over is the critical path)
   return __longlong_as_double((long long)u);
 #endif
 }
@@ -1717,8 +1719,11 @@ __device__ __forceinline__ void publish_value(double* p, double v) {
 // that land in the chunk, in child order.
 __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __restrict__ items, int nitems,
                                                  double* __restrict__ x, double* __restrict__ upd,
-                                                 double* __restrict__ ypub) {
-  const int b = blockIdx.x;
+                                                 double* __restrict__ ypub, int* __restrict__ ticket) {
+  __shared__ int s_vb;
+  if (threadIdx.x == 0) s_vb = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int b = s_vb;
   if (b >= nitems) return;
   const int s = items[4 * b], c = items[4 * b + 1];
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
@@ -1845,8 +1850,12 @@ __global__ void __launch_bounds__(256) k_fwd_big(PlanDev P, const int32_t* __res
 
 // item = (front, column block), blocks of a front in DESCENDING order.
 __global__ void __launch_bounds__(256) k_bwd_big(PlanDev P, const int32_t* __restrict__ items, int nitems,
-                                                 double* __restrict__ x, double* __restrict__ xpub) {
-  const int b = blockIdx.x;
+                                                 double* __restrict__ x, double* __restrict__ xpub,
+                                                 int* __restrict__ ticket) {
+  __shared__ int s_vb;
+  if (threadIdx.x == 0) s_vb = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int b = s_vb;
   if (b >= nitems) return;
   const int s = items[2 * b], c = items[2 * b + 1];
   const int c0 = P.scol[s], w = P.scol[s + 1] - c0;
