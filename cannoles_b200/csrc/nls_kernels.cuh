@@ -150,22 +150,27 @@ struct DenseInst {
   int n, m, nc;
   const double *At, *Bt, *Ct, *y, *e;   // the instance's arrays in HBM
   const double *Aw, *Bw;                // A and B as the evaluators read them: staged in shared memory (or = At, Bt)
+  const double* Cw;                     // C likewise (column stride nc either way)
   int ldw;                              // column stride of Aw / Bw
 };
 
 // Stage A and B of the instance into `dstA` / `dstB` (shared memory, column stride lds).  CTA-collective.
 // `phase` is the mbarrier parity of this use (the caller flips it after every call).
 template <int NT>
-__device__ __forceinline__ bool dn_stage_model(DenseInst& I, double* dstA, double* dstB, int lds,
+__device__ __forceinline__ bool dn_stage_model(DenseInst& I, double* dstA, double* dstB, double* dstC, int lds,
                                                unsigned long long* bar, uint32_t phase) {
-  const int n = I.n, m = I.m, tid = threadIdx.x;
+  const int n = I.n, m = I.m, nc = I.nc, tid = threadIdx.x;
   __syncthreads();                      // every generic-proxy access to the destination is complete
 #ifndef B2_EMULATE
-  const bool tma_ok = (m % 2 == 0) && (lds % 2 == 0) && ((reinterpret_cast<uintptr_t>(I.At) | reinterpret_cast<uintptr_t>(I.Bt)) % 16 == 0);
+  const bool tma_ok = (m % 2 == 0) && (lds % 2 == 0) && ((n * nc) % 2 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(I.At) | reinterpret_cast<uintptr_t>(I.Bt) | reinterpret_cast<uintptr_t>(I.Ct)) % 16 == 0);
   if (tma_ok) {
     if (tid < 32) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (tid == 0) mbar_expect_tx(bar, (uint32_t)(2 * n * m * sizeof(double)));
+      if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)((2 * n * m + n * nc) * sizeof(double)));
+        if (nc > 0) tma_bulk_g2s(dstC, I.Ct, (uint32_t)(n * nc * sizeof(double)), bar);
+      }
       __syncwarp();
       for (int j = tid; j < n; j += 32) {
         tma_bulk_g2s(dstA + (size_t)j * lds, I.At + (size_t)j * m, (uint32_t)(m * sizeof(double)), bar);
@@ -173,7 +178,7 @@ __device__ __forceinline__ bool dn_stage_model(DenseInst& I, double* dstA, doubl
       }
     }
     mbar_wait(bar, phase);
-    I.Aw = dstA; I.Bw = dstB; I.ldw = lds;
+    I.Aw = dstA; I.Bw = dstB; I.Cw = dstC; I.ldw = lds;
     return true;                        // the mbarrier went through one phase
   }
 #endif
@@ -183,9 +188,10 @@ __device__ __forceinline__ bool dn_stage_model(DenseInst& I, double* dstA, doubl
       dstA[(size_t)j * lds + i] = I.At[q];
       dstB[(size_t)j * lds + i] = I.Bt[q];
     }
+    for (int q = tid; q < n * nc; q += NT) dstC[q] = I.Ct[q];
     __syncthreads();
   }
-  I.Aw = dstA; I.Bw = dstB; I.ldw = lds;
+  I.Aw = dstA; I.Bw = dstB; I.Cw = dstC; I.ldw = lds;
   return false;
 }
 
@@ -229,7 +235,7 @@ __device__ __forceinline__ void dn_cons(const DenseInst& I, const double* x, dou
   const int p = tid / nc, k = tid - p * nc;
   double s = 0.0;
   if (p < npart)
-    for (int j = p; j < n; j += npart) s += I.Ct[(size_t)j * nc + k] * x[j];
+    for (int j = p; j < n; j += npart) s += I.Cw[(size_t)j * nc + k] * x[j];
   scr[tid] = s;
   __syncthreads();
   if (tid < nc) {
@@ -258,7 +264,7 @@ __device__ __forceinline__ void dn_jtprod_res(const DenseInst& I, const double* 
 
 // Jc(x)[k][j] = C[k][j] + (k == j) 0.1 x[k]
 __device__ __forceinline__ double dn_jc(const DenseInst& I, const double* x, int k, int j) {
-  const double c = I.Ct[(size_t)j * I.nc + k];
+  const double c = I.Cw[(size_t)j * I.nc + k];
   return k == j ? c + 0.1 * x[k] : c;
 }
 // out(n) = Jc(x)' lam
@@ -424,7 +430,7 @@ __global__ void __launch_bounds__(NT) k_nls_dense(BatchPlanDev P, DenseNlsModel 
 #endif
   // A and B of the instance live in the (dead) packed-triangle area while the model is evaluated
   const int lds = (m % 2 == 0) ? m + 4 : m;             // padded: conflict-free tensor-core fragment loads
-  const bool can_stage = 2 * (long long)n * lds <= P.npacked;
+  const bool can_stage = 2 * (long long)n * lds + (long long)n * nc <= P.npacked;
   uint32_t tma_phase = 0;
   bool staged = false;
   double* st = reinterpret_cast<double*>(raw + ((batched_smem_bytes(N, P.npacked) + 15) & ~(size_t)15));
@@ -464,12 +470,12 @@ __global__ void __launch_bounds__(NT) k_nls_dense(BatchPlanDev P, DenseNlsModel 
     I.Ct = M.Ct + (size_t)b * M.stride_C;
     I.y = M.y + (size_t)b * M.stride_y;
     I.e = M.e + (size_t)b * M.stride_e;
-    I.Aw = I.At; I.Bw = I.Bt; I.ldw = m;
+    I.Aw = I.At; I.Bw = I.Bt; I.Cw = I.Ct; I.ldw = m;
     staged = false;
     auto ensure_staged = [&]() {
       if (can_stage && !staged) {
         double* Pk = reinterpret_cast<double*>(raw);
-        if (dn_stage_model<NT>(I, Pk, Pk + (size_t)n * lds, lds, &mbar, tma_phase)) tma_phase ^= 1;
+        if (dn_stage_model<NT>(I, Pk, Pk + (size_t)n * lds, Pk + 2 * (size_t)n * lds, lds, &mbar, tma_phase)) tma_phase ^= 1;
         staged = true;
       }
     };
@@ -596,7 +602,7 @@ __global__ void __launch_bounds__(NT) k_nls_dense(BatchPlanDev P, DenseNlsModel 
             }
             if (stage > 0 && rho <= prm.rho_max) rho_old = rho;
             staged = false;                       // the triangle went over the staged model
-            I.Aw = I.At; I.Bw = I.Bt; I.ldw = m;
+            I.Aw = I.At; I.Bw = I.Bt; I.Cw = I.Ct; I.ldw = m;
             nfact += nfacti;
             nlinsolve++;
             if (rho > prm.rho_max || !success || cta_nonfinite<NT>(d, N) || fx >= 1e60) {
