@@ -545,7 +545,7 @@ def bench_nls(args, rank, world, local, dist, total, steps):
         chk(lib.b2_dev_malloc(C.byref(p), rec.nbytes))
         drecs.append(p)
     ms = C.c_double()
-    for k in range(min(K, 3)):          # warm the lanes (allocations happen on first use)
+    for k in range(min(K, 24)):         # warm every lane the timed legs use (a lane allocates its model buffers on first use)
         S.submit(arrs, recs[k])
     S.wait()
     sync()

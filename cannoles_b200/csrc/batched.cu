@@ -322,6 +322,14 @@ int BatchEngine::nls_init(int n, int m, int nc) {
   B2_CUDA_OK(cudaEventCreateWithFlags(&nls_start, cudaEventDisableTiming));
   for (auto& p : nls_scr)
     if (alloc(&p, (size_t)nsm * sym.nnz)) return -1;
+  // the lanes of the asynchronous verb: everything a device-resident submission needs exists before the
+  // first one (a cudaMalloc inside a stream of submissions synchronises the device and serialises them)
+  B2_CUDA_OK(cudaEventCreateWithFlags(&lane_start, cudaEventDisableTiming));
+  for (auto& L : lanes) {
+    B2_CUDA_OK(cudaStreamCreateWithFlags(&L.q, cudaStreamNonBlocking));
+    B2_CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    if (alloc(&L.scr, (size_t)nsm * sym.nnz) || alloc(&L.ticket, 1)) return -1;
+  }
   nls_ntickets = 1024;
   if (alloc(&nls_tickets, (size_t)nls_ntickets)) return -1;
   if (alloc(&nls_rec, (size_t)batch * (NLS_REC_HEAD + n + nc))) return -1;
@@ -754,12 +762,6 @@ int b2b_nls_dense_submit(b2b_handle* h, const b2_dense_nls_t* model, int64_t cou
   B2_CUDA_OK(cudaSetDevice(E.device));
   b2::BatchEngine::NlsLane& L = E.lanes[E.next_lane];
   E.next_lane = (E.next_lane + 1) % b2::BatchEngine::NLS_LANES;
-  if (!L.q) {
-    B2_CUDA_OK(cudaStreamCreateWithFlags(&L.q, cudaStreamNonBlocking));
-    B2_CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
-    if (E.alloc(&L.scr, (size_t)E.nsm * E.sym.nnz) || E.alloc(&L.ticket, 1)) return -1;
-  }
-  if (!E.lane_start) B2_CUDA_OK(cudaEventCreateWithFlags(&E.lane_start, cudaEventDisableTiming));
   const int rl = (int)b2b_nls_record_len(h);
   const bool sh = mh.shared_model != 0;
   b2_dense_nls_t md = mh;
