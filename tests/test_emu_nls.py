@@ -123,3 +123,18 @@ def test_partitioned_batch_gloo_world2(tmp_path, emu_lib):
                          capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_nan_start_is_reported_like_the_reference_error(emu_lib):
+    """`Initial point gives Inf or Nan` (src/CaNNOLeS.jl:484-487) is an error in the reference; the
+    device loop reports it as status 8 for that instance and solves the others."""
+    from cannoles_b200.batched_nls import B200BatchNLS, STATUS, pack_dense_models
+    mod = pack_dense_models(range(3), 10, 16, 3)
+    mod["x0"][1, 2] = np.nan
+    S = B200BatchNLS(3, 10, 16, 3, _lib=emu_lib)
+    try:
+        rec = S.solve(mod["At"], mod["Bt"], mod["Ct"], mod["y"], mod["e"], mod["x0"])
+    finally:
+        S.close()
+    assert [STATUS[int(s)] for s in rec[:, 0]] == ["first_order", "error: Initial point gives Inf or Nan", "first_order"]
+    assert rec[1, 2] == 0 and rec[1, 3] == 0          # no factorization, no solve
