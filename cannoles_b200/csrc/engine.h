@@ -72,10 +72,10 @@ struct Engine {
   int64_t ntflag = 0;          // tile flags of all tiled fronts; the ticket counters of the launches follow them
   int ndag = 0;
   int* d_tflag = nullptr;
-  int solve_fork = -1;   // -1: fork the solve levels only when there are no big fronts; 0 / 1: force
-  double small_max_m = 72;   // fronts up to this order take the shared-memory path (measured: 72 beats 128 and 40 on C4)
+  int solve_fork = 1;    // fork the kernel families of a solve level (round 2: with the chained big-front solves shortened by the explicit inverses forking wins on C4 too, 1.54 -> 1.47 ms); -1: only when there are no big fronts; 0: never
+  double small_max_m = 96;   // fronts up to this order take the shared-memory path (round 2 sweep on C4: 56: 3.42, 72: 3.32, 96: 3.22, 112: 3.33, 128: 3.58 ms)
   int tiny_max_m = 8;        // fronts up to this order (4 / 8 classes) take the one-thread-per-front kernels
-  int tiny_solve_max_m = 16; // ... and up to this order (16 / 32 classes) in the solves only (measured: 32 loses to a warp per front)
+  int tiny_solve_max_m = 8;  // ... and up to this order in the solves (round 2 sweep on C4: 8: 1.45, 16: 1.54, 32: 1.77 ms)
   // fronts of the multi-CTA solves with at least this many pivot blocks get explicit inverses of their
   // unit-lower 64 x 64 diagonal blocks (k_linv, at the end of the factorization): the in-block
   // substitution by one warp (2.4 k cycles on the chain of every block) becomes a mat-vec by the CTA

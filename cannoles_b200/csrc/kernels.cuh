@@ -990,6 +990,11 @@ __device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int tgid, do
     for (int idx = tid; idx < NB * LDT; idx += 256) Ts[idx] = 0.0;
   for (int eb = e0; eb < e1; eb += DAG_DESC) {
     const int cnt = min(DAG_DESC, e1 - eb);
+    // the descriptors of the previous round -- or of the previous CALL: a chain task of pivot block 1
+    // assembles tile (1, 0) and then tile (1, 1) with nothing in between -- have been read by everyone
+    // (found in round 2: without this barrier a fast warp overwrote them under a slow one, one
+    // factorization in ~100 of the C3 slice came out different; tests/test_gpu_parity.py loops on it now)
+    __syncthreads();
     if (tid < DAG_ENT * cnt) sdesc[tid] = P.tl_ent[DAG_ENT * (size_t)eb + tid];      // DAG_ENT * DAG_DESC <= 256
     __syncthreads();
     for (int k = 0; k < cnt; k++) {
@@ -1018,7 +1023,6 @@ __device__ __forceinline__ void dag_assemble_tile(const PlanDev& P, int tgid, do
         B2_UNROLL
         for (int cc = 0; cc < 2; cc++) { cold[a][cc][0] += v[a][cc][0]; cold[a][cc][1] += v[a][cc][1]; }
     }
-    if (eb + DAG_DESC < e1) __syncthreads();     // the descriptors are overwritten by the next round
   }
   if (f1 <= f0) return;
   for (int fb = f0; fb < f1; fb += DAG_STAGE) {

@@ -333,3 +333,22 @@ def test_inspection_entry_points(ctor, gpu_lib):
     buf = np.zeros(1 << 16)
     assert gpu_lib.b2_host_register(buf.ctypes.data_as(C.c_void_p), buf.nbytes) == 0
     assert gpu_lib.b2_host_unregister(buf.ctypes.data_as(C.c_void_p)) == 0
+
+
+def test_factorization_is_bit_reproducible_over_many_runs(ctor, monkeypatch):
+    """300 factorizations of the 5000-camera slice of config 3 with EVERY tiled front on the dataflow
+    kernel (B2_DAG_MIN_NP = 1): pivots and inertia identical bit for bit.  Round 2 found a write-after-
+    read race on the child descriptors of k_front_dag this way (one run in ~100 differed)."""
+    from cannoles_b200.workloads import first_system, make_config
+    monkeypatch.setenv("B2_DAG_MIN_NP", "1")
+    nls, method, _ = make_config("c3", 5000)
+    s, rhs = first_system(nls, method, functools.partial(ctor, nvar=nls.nvar, nequ=nls.nequ, ncon=nls.ncon,
+                                                         shift_retries=False))
+    B = s.LDLT
+    ok0 = B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS)
+    d0, i0 = B.factor.d.copy(), B.last_inertia
+    for _ in range(300):
+        assert B.try_to_factorize(s.vals, nls.nvar, nls.nequ, nls.ncon, EPS) == ok0
+        assert B.last_inertia == i0
+        assert np.array_equal(B.factor.d, d0, equal_nan=True)
+    B.close()
