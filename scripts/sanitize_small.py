@@ -40,3 +40,12 @@ ok3 = Bt.try_to_factorize(vals)
 Bt.solve_ldl(rhs, d)
 print("batched", ok, ok3, float(np.abs(d).max()))
 Bt.close()
+
+# the device-resident batched loop (k_nls_dense: TMA staging, CGLS, line search via a far start)
+from cannoles_b200.batched_nls import B200BatchNLS, pack_dense_models  # noqa: E402
+mod = pack_dense_models(range(2))
+mod["x0"][1] *= 10.0
+S = B200BatchNLS(2)
+rec = S.solve(mod["At"], mod["Bt"], mod["Ct"], mod["y"], mod["e"], mod["x0"])
+print("nls status", rec[:, 0], "iter", rec[:, 1], "nfact", rec[:, 2], "nbk", rec[:, 4])
+S.close()
