@@ -387,7 +387,12 @@ int Engine::build_plan() {
       // blocks).  The key is then raised above the keys of everything the task waits for, so that
       // sorting by key stays a topological order: a CTA only ever waits for smaller tickets.
       {
-        constexpr double T_ASM = 8, T_UPD = 2.5, T_LDL = 12.5, T_SUB = 5, T_POST = 2, T_ST = 1, T_EPS = 1e-3;
+        // (cost model in us; T_UPD is per 64-column pivot block applied to a tile.  Developer knobs
+        // B2_DAG_TUPD / B2_DAG_TASM override the two that the task traces disagree with most.)
+        double T_ASM = 8, T_UPD = 2.5;
+        constexpr double T_LDL = 12.5, T_SUB = 5, T_POST = 2, T_ST = 1, T_EPS = 1e-3;
+        if (const char* e = getenv("B2_DAG_TUPD")) T_UPD = atof(e);
+        if (const char* e = getenv("B2_DAG_TASM")) T_ASM = atof(e);
         struct FS { double R = 0, KR = 0; std::vector<double> F, KF, Y, KY; };
         const int df0 = fg.empty() ? 0 : fg[0].df;
         std::vector<FS> fs(fg.size());
