@@ -46,9 +46,9 @@ METRIC = "kkt_factor_solve_per_s"
 UNIT = "KKT factor+solve/s"
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE factorization (all its kernels), from the ncu
-# capture summarised in profiles/traffic_r02_a.txt; only valid for the default workload
-KNOWN_TRAFFIC = {("c4", None, "nd"): 1548.7e6}
-TRAFFIC_SOURCE = "profiles/traffic_r02_a.txt"
+# capture summarised in profiles/traffic_r02_i.txt; only valid for the default workload
+KNOWN_TRAFFIC = {("c4", None, "nd"): 1424.0e6}
+TRAFFIC_SOURCE = "profiles/traffic_r02_i.txt"
 
 
 # ------------------------------------------------------------------------------------------

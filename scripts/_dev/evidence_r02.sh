@@ -1,5 +1,5 @@
 # round-2 evidence: GPU tests, launch list with DRAM traffic, ncu --set full of the top kernels, bench lines
-mkdir -p gpurun_out/r3c; O=gpurun_out/r3c
+mkdir -p gpurun_out/r3t; O=gpurun_out/r3t
 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_gpu.log
 python bench.py --steps 20 --warmup 5 > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"
 python scripts/profile_launches.py c4 512 0 v > $O/warm_c4.txt 2>&1
