@@ -516,7 +516,10 @@ def bench_nls(args, rank, world, local, dist, total, steps):
         S.kkt.register_host(a)
     ptrs = S.upload(*arrs)
     h = S.kkt._h
-    K = steps
+    # batches in flight: a rank's share of a batch shrinks with the number of ranks but the slowest
+    # instance of the batch does not (its chain of ~1300 Newton systems takes ~0.1 s on one SM), so the
+    # stream of batches has to be long enough for the other SMs to have work meanwhile
+    K = min(128, max(steps, 16 * world))
 
     def chk(rc):
         if rc != 0:
@@ -545,7 +548,7 @@ def bench_nls(args, rank, world, local, dist, total, steps):
         chk(lib.b2_dev_malloc(C.byref(p), rec.nbytes))
         drecs.append(p)
     ms = C.c_double()
-    for k in range(min(K, 24)):         # warm every lane the timed legs use (a lane allocates its model buffers on first use)
+    for k in range(K):                  # warm every lane the timed legs use (a lane allocates its buffers on first use)
         S.submit(arrs, recs[k])
     S.wait()
     sync()
@@ -612,7 +615,7 @@ def bench_nls(args, rank, world, local, dist, total, steps):
             "latency_ms": {"one_batch_device_resident": lat_dev, "one_batch_host_arrays": lat_host,
                            "note": "bounded by the slowest instance of the batch (instance %d: %d factorizations, %d line-search "
                                    "backtracks); batches in flight fill the SMs it leaves idle" % (slow, allrec[slow, 2], allrec[slow, 4])},
-            "steps": K, "batches_in_flight": min(K, 24), "n_gpus": world, "scaling": "strong",
+            "steps": K, "batches_in_flight": K, "n_gpus": world, "scaling": "strong",
             "config": {"workload": "c5: %d independent constrained NLS (n=64, m=128, 16 constraints), multi-start x0 ~ N(0,1), "
                                    "solved to the reference's default tolerances" % total,
                        "batch_total": total, "batch_per_rank": nb, "params": "ParamCaNNOLeS / solve! defaults (max_time = Inf)"},

@@ -57,7 +57,7 @@ struct BatchEngine {
   // (its H2D, its kernel, its D2H in stream order, own model buffers / scratch / ticket), successive
   // submissions on successive lanes, so that batches overlap: the copy engines of one with the SMs of
   // another, and the SMs a batch leaves idle while its slowest instance finishes with the next batch
-  static constexpr int NLS_LANES = 24;
+  static constexpr int NLS_LANES = 128;
   struct NlsLane {
     cudaStream_t q = nullptr;
     cudaEvent_t done = nullptr;
@@ -325,7 +325,8 @@ int BatchEngine::nls_init(int n, int m, int nc) {
   // the lanes of the asynchronous verb: everything a device-resident submission needs exists before the
   // first one (a cudaMalloc inside a stream of submissions synchronises the device and serialises them)
   B2_CUDA_OK(cudaEventCreateWithFlags(&lane_start, cudaEventDisableTiming));
-  for (auto& L : lanes) {
+  for (int i = 0; i < NLS_LANES; i++) {
+    NlsLane& L = lanes[i];
     B2_CUDA_OK(cudaStreamCreateWithFlags(&L.q, cudaStreamNonBlocking));
     B2_CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
     if (alloc(&L.scr, (size_t)nsm * sym.nnz) || alloc(&L.ticket, 1)) return -1;
@@ -817,7 +818,8 @@ int b2b_nls_wait(b2b_handle* h) {
       L.pending = false;
     }
   B2_CUDA_OK(cudaStreamSynchronize(E.stream));
-  return 0;
+  E.next_lane = 0;    // everything is complete: the next stream of submissions starts on the first lane again
+  return 0;           // (so that a repeated stream of K batches reuses the K model buffers it has allocated)
 }
 
 int b2b_free(b2b_handle* h) {

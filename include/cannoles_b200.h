@@ -212,7 +212,7 @@ int b2b_nls_dense_solve_dev(b2b_handle* h, const b2_dense_nls_t* model_dev, int6
 int b2b_nls_dense_solve(b2b_handle* h, const b2_dense_nls_t* model_host, int64_t count,
                         const b2_nls_params_t* params, double* records, int64_t chunk);
 /* Asynchronous form: queue one batch (upload, solve, download in stream order on one of the
- * handle's 24 lanes) and return; b2b_nls_wait blocks until every queued batch is complete.
+ * handle's 128 lanes) and return; b2b_nls_wait blocks until every queued batch is complete.
  * Batches in flight overlap: PCIe of one with the SMs of another, and the SMs a batch leaves idle
  * while its slowest instance finishes are taken by the next batch.  where = 0: *model and records
  * are host memory (pin them); where = 1: device memory.  Arrays stay untouched until the wait. */
