@@ -150,3 +150,58 @@ function solve_ldl!(rhs::Vector{Float64}, factor::B200Factor, d::Vector{Float64}
     factor.handle, rhs, d, 1, factor.refine_steps, C_NULL))
   return true
 end
+
+# ------------------------------------------------------------------------------------------
+# Batches of small dense instances that share one KKT pattern (multi-start / per-sample
+# estimation; BASELINE.json config 5): the WHOLE iteration of solve! (src/CaNNOLeS.jl:418-864) runs
+# on the device, one CTA per instance (csrc/nls_kernels.cuh).  The reference has no batch entry
+# point; this is the one a maintainer would put next to `cannoles`.  Never executed in this
+# repository's CI (no Julia offline); the C side is exercised through the same symbols from Python
+# (cannoles_b200/batched_nls.py, tests/test_gpu_nls.py).
+#   F(x) = A x + 0.1 sin(B x) - y,   c(x) = C x + 0.05 (x .* x)[1:ncon] - e = 0
+#   A, B :: Array{Float64,3} of size (m, n, batch), C :: (ncon, n, batch)   (column-major = the C side's layout)
+struct B2NLSParams                      # b2_nls_params_t
+  eig_tol::Float64; delta_min::Float64; kappa_dec::Float64; kappa_inc::Float64; kappa_largeinc::Float64
+  rho0::Float64; rho_max::Float64; rho_min::Float64; gamma_A::Float64
+  atol::Float64; rtol::Float64; Fatol::Float64; Frtol::Float64; delta_dec::Float64; cgls_tol::Float64
+  max_iter::Int32; max_eval::Int32; max_inner::Int32; always_accept_extrapolation::Int32
+  use_initial_multiplier::Int32; reserved::Int32
+end
+struct B2DenseNLS                       # b2_dense_nls_t
+  n::Int64; m::Int64; ncon::Int64; shared_model::Int64
+  At::Ptr{Float64}; Bt::Ptr{Float64}; Ct::Ptr{Float64}; y::Ptr{Float64}; e::Ptr{Float64}
+  x0::Ptr{Float64}; y0::Ptr{Float64}
+end
+
+"""
+    cannoles_batch(A, B, C, y, e, x0; rows, cols) -> records
+
+`rows`, `cols`: the COO layout of the Newton system of ONE instance (src/CaNNOLeS.jl:281-315, exact
+residual Hessian).  `records[:, b]` = status, iter, nfact, nlinsolve, nbk, neval_residual, neval_cons,
+objective, ||c||, ||dual||_inf, rho, delta, x (n), lambda (ncon) of instance `b` (status: 1 first_order,
+2 small_residual, 3 stalled, 4 exception, 5 max_eval, 7 max_iter; 8-10 = the errors solve! throws).
+"""
+function cannoles_batch(A::Array{Float64,3}, B::Array{Float64,3}, C::Array{Float64,3}, y::Matrix{Float64},
+                        e::Matrix{Float64}, x0::Matrix{Float64}; rows::Vector{Int64}, cols::Vector{Int64},
+                        device::Integer = 0)
+  m, n, batch = size(A)
+  ncon = size(C, 1)
+  N = n + m + ncon
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  b200_check(ccall((:b2b_analyze, libb200), Cint,
+    (Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Int64, Int64, Cint, Ptr{Int64}, Cint, Ptr{Ptr{Cvoid}}),
+    N, length(rows), rows, cols, n, m, ncon, batch, 3, C_NULL, device, h))      # 3 = B2_ORDER_AMD
+  prm = Ref{B2NLSParams}()
+  ccall((:b2_nls_default_params, libb200), Cvoid, (Ptr{B2NLSParams},), prm)
+  reclen = ccall((:b2b_nls_record_len, libb200), Int64, (Ptr{Cvoid},), h[])
+  rec = Matrix{Float64}(undef, reclen, batch)
+  GC.@preserve A B C y e x0 begin
+    md = Ref(B2DenseNLS(n, m, ncon, 0, pointer(A), pointer(B), pointer(C), pointer(y), pointer(e),
+                        pointer(x0), C_NULL))
+    rc = ccall((:b2b_nls_dense_solve, libb200), Cint,
+      (Ptr{Cvoid}, Ptr{B2DenseNLS}, Int64, Ptr{B2NLSParams}, Ptr{Float64}, Int64), h[], md, batch, prm, rec, 0)
+  end
+  ccall((:b2b_free, libb200), Cint, (Ptr{Cvoid},), h[])
+  b200_check(rc)
+  return rec
+end
