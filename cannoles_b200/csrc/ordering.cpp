@@ -29,6 +29,19 @@ bool order_metis_nd(int64_t n, const std::vector<int64_t>& xadj, const std::vect
   int64_t options[40];
   METIS_SetDefaultOptions(options);
   options[17] = 0;  // METIS_OPTION_NUMBERING = C-style
+  if (const char* e = getenv("B2_METIS_OPTS")) {   // developer knob: "index=value,index=value" (METIS 5.1 option indices)
+    const char* q = e;
+    while (*q) {
+      char* end = nullptr;
+      const long idx = strtol(q, &end, 10);
+      if (end == q || *end != '=') break;
+      q = end + 1;
+      const long val = strtol(q, &end, 10);
+      if (end == q) break;
+      if (idx >= 0 && idx < 40) options[idx] = val;
+      q = (*end == ',') ? end + 1 : end;
+    }
+  }
   int64_t nv = n;
   int rc = METIS_NodeND(&nv, xa.data(), ad.data(), nullptr, options, p.data(), ip.data());
   if (rc != 1) { err = "METIS_NodeND failed"; return false; }
