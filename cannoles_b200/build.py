@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libcannoles_b200.so")
 SOURCES = ["engine.cu", "capi.cu", "batched.cu", "measure.cu", "symbolic.cpp", "ordering.cpp"]
-HEADERS = ["kernels.cuh", "batched_kernels.cuh", "nls_kernels.cuh", "mma.cuh", "engine.h", "plan.h", "symbolic.h", "b2_cuda.h",
+HEADERS = ["kernels.cuh", "batched_kernels.cuh", "nls_kernels.cuh", "ldlt_packed.cuh", "mma.cuh", "engine.h", "plan.h", "symbolic.h", "b2_cuda.h",
            os.path.join("..", "..", "include", "cannoles_b200.h")]
 METIS = "/usr/local/cuda/lib64/libmetis_static.a"
 
