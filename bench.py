@@ -356,7 +356,7 @@ def measure_system(lib, args, workload, size, ordering_name, steps, warmup, loca
     cfg_args = argparse.Namespace(workload=workload, size=size)
     return {"value": world * steps / (dev_ms * 1e-3), "ms_per_step": dev_ms / steps,
             "config": config_dict(cfg_args, desc, st, {
-                "hessian_mode": method, "ordering": ordering_name, "refine_steps_max": args.refine, "refine_tol": 1e-13,
+                "hessian_mode": method, "ordering": ordering_name, "refine_steps_max": args.refine, "refine_tol": B.refine_tol,
                 "solve_sweeps_used": nsw, "rho": rho_used, "rho_reason": rho_reason, "nsuper": int(st["nsuper"]), "nlevels": int(st["nlevels"]),
                 "max_front": int(st["max_front"]), "parallelism": f"replicas x{world}"}),
             "phase_ms": {"assemble": ph[0], "factor": ph[1], "solve": ph[2]},

@@ -133,7 +133,7 @@ struct Engine {
   cudaGraphExec_t g_fact = nullptr, g_fwdbwd = nullptr;
 #endif
   bool use_graph = true;
-  double refine_tol = 0.0;  // > 0: stop refining as soon as ||K x - b|| / ||b|| <= refine_tol
+  double refine_tol = 5e-13;  // > 0: stop refining as soon as ||K x - b|| / ||b|| <= refine_tol (north-star bar 1e-12); 0: always refine_steps sweeps
   int last_sweeps = 0;      // forward/backward sweeps used by the last solve
   std::vector<void*> registered;
 

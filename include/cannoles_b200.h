@@ -104,7 +104,8 @@ int b2_factorize_retry(b2_handle* h, const double* vals, double rho, double eig_
 int b2_solve(b2_handle* h, const double* rhs, double* d_out, int negate, int refine_steps,
              double* relres);
 /* forward/backward sweeps the last solve used (1 + refinement sweeps actually taken); with
- * b2_set_option(h, "refine_tol", tol > 0) refinement stops as soon as the residual is <= tol */
+ * b2_set_option(h, "refine_tol", tol): refinement stops as soon as the residual is <= tol (default 5e-13;
+ * 0: always refine_steps sweeps) */
 int b2_last_sweeps(const b2_handle* h);
 
 /* Device-resident variants (inputs/outputs already in HBM); used to time the kernels alone. */
