@@ -31,7 +31,8 @@ int dalloc(T** dptr, size_t n, double& bytes) {
   return 0;
 }
 
-int small_class(int m) { return m <= 16 ? 0 : (m <= 40 ? 1 : (m <= 72 ? 2 : 3)); }
+int g_small_c0_max = 16;   // fronts up to this order: one warp per front, four fronts per CTA (developer knob B2_SMALL_C0_MAX)
+int small_class(int m) { return m <= g_small_c0_max ? 0 : (m <= 40 ? 1 : (m <= 72 ? 2 : 3)); }
 int solve_class(int m) { return m <= 32 ? 0 : (m <= 128 ? 1 : (m <= 512 ? 2 : 3)); }
 
 double wall() {
@@ -41,6 +42,7 @@ double wall() {
 }  // namespace
 
 int Engine::build_plan() {
+  if (const char* e = getenv("B2_SMALL_C0_MAX")) g_small_c0_max = std::max(8, std::min(40, atoi(e)));
   const Symbolic& S = sym;
   if (S.uptr[S.nsuper] >= (int64_t)INT32_MAX) {
     snprintf(g_last_error, sizeof(g_last_error), "update-vector storage exceeds int32 offsets");
