@@ -64,6 +64,7 @@ int b2_analyze(int64_t N, int64_t nnz, const int64_t* rows1, const int64_t* cols
   if (const char* e = getenv("B2_DAG_SCHED")) h->eng.dag_sched = atoi(e) != 0;
   if (const char* e = getenv("B2_SOLVE_BIG_M")) h->eng.solve_big_m = atof(e);
   if (const char* e = getenv("B2_INV_MIN_BLK")) h->eng.inv_min_blk = atoi(e);
+  if (const char* e = getenv("B2_UPDATE_TMA")) h->eng.update_tma = atoi(e) != 0;
   if (const char* e = getenv("B2_TINY_MAX_M")) h->eng.tiny_max_m = std::min(8, atoi(e));
   if (const char* e = getenv("B2_TINY_SOLVE_MAX_M")) h->eng.tiny_solve_max_m = std::min(32, atoi(e));
   if (h->eng.init(device)) {

@@ -784,7 +784,7 @@ int Engine::init(int dev) {
   if (upload(&d_Sp, S.Sp, bytes_device)) return -1;
   if (upload(&d_Sj, S.Sj, bytes_device)) return -1;
   if (upload(&d_Sslot, S.Sslot, bytes_device)) return -1;
-  if (dalloc(&d_Lx, (size_t)S.nnzL_store, bytes_device)) return -1;
+  if (dalloc(&d_Lx, (size_t)S.nnzL_store + 8, bytes_device)) return -1;   // + 8: the bulk copies of k_update read up to two doubles past a tile
   if (dalloc(&d_CB, (size_t)S.cb_store, bytes_device)) return -1;
   if (dalloc(&d_dvec, (size_t)S.N, bytes_device)) return -1;
   if (dalloc(&d_counts, 8, bytes_device)) return -1;
@@ -875,7 +875,8 @@ int Engine::launch_one(const Launch& L, cudaStream_t st) {
       B2_LAUNCH(k_diag_writeback, L.count, 256, 0, st, plan, it, L.count);
       break;
     case LK_UPDATE:
-      B2_LAUNCH(k_update, L.count, 256, 0, st, plan, it, L.count, L.jb, NB, L.mode, L.flag);
+      if (update_tma) B2_LAUNCH(k_update<true>, L.count, 256, 0, st, plan, it, L.count, L.jb, NB, L.mode, L.flag);
+      else B2_LAUNCH(k_update<false>, L.count, 256, 0, st, plan, it, L.count, L.jb, NB, L.mode, L.flag);
       break;
     case LK_DAG:
       // few tasks (the top of the tree): one CTA per SM -- asking for more than half of the shared

@@ -80,6 +80,7 @@ struct Engine {
   // unit-lower 64 x 64 diagonal blocks (k_linv, at the end of the factorization): the in-block
   // substitution by one warp (2.4 k cycles on the chain of every block) becomes a mat-vec by the CTA
   int inv_min_blk = 2;
+  bool update_tma = false;   // k_update<true>: operand tiles by TMA bulk copies (B2_UPDATE_TMA=1; measured slower on C3, see kernels.cuh)
   double solve_big_m = 96;   // fronts above this order take the multi-CTA solve kernels (measured: 96 < 192 < 384)
 
   // device buffers

@@ -738,6 +738,11 @@ __global__ void __launch_bounds__(256) k_diag_writeback(PlanDev P, const int32_t
 //   mode 0 (inside the panel): rows/cols start at org = k0+K, cols < w, C is the panel itself
 //          (the next diagonal block is factored by the following k_trsm);
 //   mode 1 (contribution block): org = w, cols < m, C is CB (lower triangle), K = w.
+// TMA = true: the operand tiles arrive by cp.async.bulk + mbarrier instead of LDG -> registers -> STS
+// (selected with B2_UPDATE_TMA=1; measured on C3, 66 k tiles of K = 9 .. 27 ... 249: 1.64 ms against
+// 1.50 ms for the register-staged pipeline, which therefore stays the default -- the tiles are 16
+// columns of 512 bytes per chunk, too small for the copy engine to beat 256 threads loading them)
+template <bool TMA>
 __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __restrict__ items, int nitems, int k0,
                                                    int Kreq, int mode, int skipdiag) {
   const int b = blockIdx.x;
@@ -753,8 +758,8 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
   const int i0 = org + ti * TILE, j0 = org + tj * TILE;
   const int nbnext = (mode == 0) ? min(NB, w - org) : 0;   // rows of the next pivot block: [org, org + nbnext)
   constexpr int KC = UPD_KC, LDT = TILE + 4;
-  __shared__ double As[2][KC][LDT];
-  __shared__ double Bs[2][KC][LDT];
+  __shared__ __align__(16) double As[2][KC][LDT];
+  __shared__ __align__(16) double Bs[2][KC][LDT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp & 1, wc = warp >> 1;           // warp tile: rows wr*32.., cols wc*16..
@@ -763,15 +768,101 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
   for (int a = 0; a < 4; a++)
     B2_UNROLL
     for (int c = 0; c < 2; c++) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
+  const int nchunk = (K + KC - 1) / KC;
+  const double* dv = P.dvec + c0 + k0;
+  double* Cb = (mode == 0) ? Lp : (P.CB + P.cbptr[s]);
+  double cold[4][2][2];
+  auto load_c = [&]() {   // the C tile is read early (its latency hides behind the K loop) and written once at the end
+    B2_UNROLL
+    for (int a = 0; a < 4; a++)
+      B2_UNROLL
+      for (int cc = 0; cc < 2; cc++)
+        B2_UNROLL
+        for (int e = 0; e < 2; e++) {
+          const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
+          const bool ok = ri < m && cj < jend && ri >= cj;
+          const double* src = (mode == 0) ? (Cb + ri + (size_t)cj * m) : (Cb + (ri - w) + (size_t)(cj - w) * r);
+          cold[a][cc][e] = ok ? *src : 0.0;
+        }
+  };
+#ifndef B2_EMULATE
+  if constexpr (TMA) {
+  // ---- operand pipeline by TMA: one cp.async.bulk per column of the A and of the B tile (64 rows = 512
+  // bytes, contiguous in the column-major panel) straight into shared memory, completion on an mbarrier
+  // per buffer; nothing is staged in registers.  A column starts at Lp + i0 + k m, which is 16-byte
+  // aligned only when that offset is even: the copy starts at the even address at or below it and is
+  // 66 doubles long, and the fragment loads add the column's shift (0 or 1).  The rows a partial tile
+  // does not have (and the one or two doubles around the 64) are whatever sits there in the panel: they
+  // only reach rows / columns of C that are not stored.  Columns k >= K of the last chunk are masked
+  // in the fragment loads.  d_k goes to shared memory by plain loads and scales the B fragments.
+  __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ double ds[2][KC];
+  const long long offA = (long long)P.lptr[s] + i0 + (long long)k0 * m, offB = (long long)P.lptr[s] + j0 + (long long)k0 * m;
+  const int mpar = m & 1;
+  const int shA0 = (int)(offA & 1), shB0 = (int)(offB & 1);
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  __syncthreads();
+  auto issue = [&](int c) {   // warp 0: lanes 0..15 the A columns of chunk c, lanes 16..31 the B columns
+    const int buf = c & 1, kc = c * KC;
+    const int nk = min(KC, K - kc);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the generic-proxy reads of this buffer are behind us
+    if (lane == 0) mbar_expect_tx(&bar[buf], (uint32_t)(2 * nk * 66 * sizeof(double)));
+    __syncwarp();
+    const int kk = lane & 15;
+    if (kk < nk) {
+      const bool isB = lane >= 16;
+      const long long off = (isB ? offB : offA) + (long long)(kc + kk) * m;
+      const double* src = P.Lx + (off & ~1LL);
+      double* dst = isB ? &Bs[buf][kk][0] : &As[buf][kk][0];
+      tma_bulk_g2s(dst, src, (uint32_t)(66 * sizeof(double)), &bar[buf]);
+    }
+  };
+  auto load_d = [&](int c) {
+    if (tid < KC) { const int k = c * KC + tid; ds[c & 1][tid] = k < K ? dv[k] : 0.0; }
+  };
+  B2_TICK(20);
+  if (warp == 0) issue(0);
+  load_d(0);
+  load_c();
+  __syncthreads();                       // ds[0]
+  B2_TICK(21);
+  uint32_t ph0 = 0, ph1 = 0;
+  for (int c = 0; c < nchunk; c++) {
+    const int buf = c & 1, kc = c * KC;
+    if (c + 1 < nchunk) {                // buffer buf ^ 1 was released by the barrier that ended chunk c - 1
+      if (warp == 0) issue(c + 1);
+      load_d(c + 1);
+    }
+    mbar_wait(&bar[buf], buf ? ph1 : ph0);
+    if (buf) ph1 ^= 1; else ph0 ^= 1;
+    B2_UNROLL
+    for (int ks = 0; ks < KC; ks += 4) {
+      const int k = ks + t;
+      const bool kv = kc + k < K;
+      const int sa = (shA0 + (kc + k) * mpar) & 1, sb = (shB0 + (kc + k) * mpar) & 1;
+      const double dk = ds[buf][k];
+      double af[4], bf[2];
+      B2_UNROLL
+      for (int a = 0; a < 4; a++) af[a] = kv ? As[buf][k][wr * 32 + a * 8 + g + sa] : 0.0;
+      B2_UNROLL
+      for (int cc = 0; cc < 2; cc++) bf[cc] = kv ? Bs[buf][k][wc * 16 + cc * 8 + g + sb] * dk : 0.0;
+      B2_UNROLL
+      for (int a = 0; a < 4; a++)
+        B2_UNROLL
+        for (int cc = 0; cc < 2; cc++) dmma_8x8x4(acc[a][cc][0], acc[a][cc][1], af[a], bf[cc]);
+    }
+    __syncthreads();                     // chunk c has been read by everyone: its buffer may be refilled; ds[buf ^ 1] is complete
+  }
+  } else
+#endif
+  {
   // loader: each thread moves KC/4 (k) x 1 (row) elements of A and of B per chunk
   const int lr = tid & 63, lk = tid >> 6;
   const int gi = i0 + lr, gj = j0 + lr;
   const bool vi = gi < m, vj = gj < jend;
   const double* pa = Lp + gi + (size_t)k0 * m;
   const double* pb = Lp + gj + (size_t)k0 * m;
-  const double* dv = P.dvec + c0 + k0;
   double ra[KC / 4], rb[KC / 4], rk[KC / 4];
-  const int nchunk = (K + KC - 1) / KC;
   // the loads only: the product with d_k is formed when the registers go to shared memory, one
   // chunk of tensor work later (a multiply here would wait for the loads it is meant to hide)
   auto gload = [&](int kc) {
@@ -792,20 +883,7 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
   };
   B2_TICK(20);
   gload(0);
-  // the C tile is read now (its latency hides behind the K loop) and written once at the end
-  double* Cb = (mode == 0) ? Lp : (P.CB + P.cbptr[s]);
-  double cold[4][2][2];
-  B2_UNROLL
-  for (int a = 0; a < 4; a++)
-    B2_UNROLL
-    for (int cc = 0; cc < 2; cc++)
-      B2_UNROLL
-      for (int e = 0; e < 2; e++) {
-        const int ri = i0 + wr * 32 + a * 8 + g, cj = j0 + wc * 16 + cc * 8 + 2 * t + e;
-        const bool ok = ri < m && cj < jend && ri >= cj;
-        const double* src = (mode == 0) ? (Cb + ri + (size_t)cj * m) : (Cb + (ri - w) + (size_t)(cj - w) * r);
-        cold[a][cc][e] = ok ? *src : 0.0;
-      }
+  load_c();
   sstore(0);
   __syncthreads();
   B2_TICK(21);
@@ -826,6 +904,7 @@ __global__ void __launch_bounds__(256, 2) k_update(PlanDev P, const int32_t* __r
     }
     if (c + 1 < nchunk) sstore(buf ^ 1);
     __syncthreads();
+  }
   }
   B2_TICK(22);
   B2_UNROLL
